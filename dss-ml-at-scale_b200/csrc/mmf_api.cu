@@ -1,0 +1,543 @@
+// mmf_api.cu -- the C ABI of libmmf.so (include/mmf.h): context, design plan (float64 calendar
+// whitening on the host), kernel dispatch, and the pipelined host-buffer path.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mmf_internal.cuh"
+
+using namespace mmf;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU_TRY(expr)                                                                              \
+  do {                                                                                            \
+    cudaError_t e__ = (expr);                                                                     \
+    if (e__ != cudaSuccess)                                                                       \
+      return fail(MMF_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// 2-D fp32 tensor map: dims {inner, outer}, row pitch in bytes, box {box_inner, box_outer}, 128-B swizzle
+int encode_2d(void* out128, const void* gptr, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+              uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(MMF_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(reinterpret_cast<CUtensorMap*>(out128), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(gptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MMF_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return MMF_OK;
+}
+
+struct Plan {
+  bool valid = false;
+  int32_t n_rows = 0, n_rows_pad = 0, t_fit = 0, t_pad = 0, has_constant = 0;
+  uint32_t kept_mask = 0;
+  double W[P * P];
+  float4* d_a4 = nullptr;
+  float* d_at = nullptr;
+  float* d_apred = nullptr;
+  float* d_w = nullptr;
+  alignas(64) unsigned char tmap_at[128];
+};
+
+constexpr int NBUF = 3;
+
+struct Staging {
+  float* d_y = nullptr;      size_t y_cap = 0;        // bytes
+  float* d_out = nullptr;    size_t out_cap = 0;
+  float* d_beta = nullptr;   size_t beta_cap = 0;
+  int32_t* d_status = nullptr; size_t status_cap = 0;
+  cudaEvent_t ev_h2d = nullptr, ev_comp = nullptr, ev_d2h = nullptr;
+};
+
+}  // namespace
+
+struct mmf_ctx {
+  int device = 0;
+  int sm_count = 0;
+  mmf_config cfg{};
+  cudaStream_t stream = nullptr;       // compute stream (owned or borrowed)
+  bool own_stream = false;
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+  uint32_t* d_pending = nullptr;
+  int32_t* d_status_scratch = nullptr;
+  size_t status_scratch_cap = 0;
+  Plan plan;
+  Staging st[NBUF];
+};
+
+namespace {
+
+void free_plan(Plan& p) {
+  cudaFree(p.d_a4); cudaFree(p.d_at); cudaFree(p.d_apred); cudaFree(p.d_w);
+  p = Plan{};
+}
+
+int grow(void** ptr, size_t* cap, size_t need) {
+  if (*cap >= need) return MMF_OK;
+  if (*ptr) cudaFree(*ptr);
+  *ptr = nullptr; *cap = 0;
+  cudaError_t e = cudaMalloc(ptr, need);
+  if (e != cudaSuccess) return fail(MMF_E_NOMEM, "cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e));
+  *cap = need;
+  return MMF_OK;
+}
+
+bool is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+DesignView view_of(const Plan& p) {
+  DesignView d;
+  d.a4 = p.d_a4; d.at = p.d_at; d.apred = p.d_apred; d.w = p.d_w;
+  d.n_rows = p.n_rows; d.n_rows_pad = p.n_rows_pad; d.t_fit = p.t_fit; d.t_pad = p.t_pad;
+  d.kept_mask = p.kept_mask; d.has_constant = p.has_constant;
+  return d;
+}
+
+// Enqueue the fit for device-resident buffers on `s`.  status must be non-null.
+int run_device(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, int32_t pred_start, int32_t n_pred,
+               float* out, int64_t ld_out, float* beta, int32_t* status, cudaStream_t s, int* launches,
+               int* kernel_used) {
+  const DesignView d = view_of(ctx->plan);
+  FitArgs a{};
+  a.y = y; a.n = n; a.ld_y = ld_y; a.pred_start = pred_start; a.n_pred = n_pred;
+  a.out = out; a.ld_out = ld_out; a.out_beta = beta; a.status = status;
+  a.only_pending = 0; a.pending_count = nullptr;
+  const char* why = nullptr;
+  int kernel = ctx->cfg.kernel;
+  const bool tc_ok = fit_tc_supported(d, a, &why);
+  if (kernel == MMF_KERNEL_TC && !tc_ok) return fail(MMF_E_UNSUPPORTED, "tcgen05 kernel not applicable: %s", why);
+  if (kernel == MMF_KERNEL_AUTO) kernel = tc_ok ? MMF_KERNEL_TC : MMF_KERNEL_WARP;
+  if (kernel == MMF_KERNEL_TC) {
+    TcLaunch tl;
+    int rc = encode_2d(tl.tmap_y, y, (uint64_t)d.t_fit, (uint64_t)n, (uint64_t)ld_y * 4, 32, 128);
+    if (rc != MMF_OK) return rc;
+    memcpy(tl.tmap_at, ctx->plan.tmap_at, 128);
+    CU_TRY(cudaMemsetAsync(ctx->d_pending, 0, sizeof(uint32_t), s));
+    CU_TRY(launch_fit_tc(d, a, tl, ctx->d_pending, ctx->sm_count, s));
+    ++*launches;
+    if (!ctx->cfg.assume_finite) {
+      FitArgs m = a;
+      m.only_pending = 1;
+      m.pending_count = ctx->d_pending;
+      CU_TRY(launch_fit_warp(d, m, ctx->sm_count, s));
+      ++*launches;
+    }
+  } else {
+    CU_TRY(launch_fit_warp(d, a, ctx->sm_count, s));
+    ++*launches;
+  }
+  *kernel_used = kernel;
+  return MMF_OK;
+}
+
+}  // namespace
+
+// =============================================================================
+extern "C" {
+
+int mmf_version(void) { return MMF_VERSION; }
+
+const char* mmf_last_error(void) { return g_err.c_str(); }
+
+int mmf_device_count(int32_t* count) {
+  if (!count) return fail(MMF_E_INVALID, "count is NULL");
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) { cudaGetLastError(); c = 0; }
+  *count = c;
+  return MMF_OK;
+}
+
+int mmf_create(const mmf_config* cfg, mmf_ctx** out) {
+  if (!out) return fail(MMF_E_INVALID, "out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(MMF_E_CUDA, "no CUDA device available (%s); libmmf has no CPU path",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  }
+  mmf_ctx* ctx = new mmf_ctx();
+  if (cfg) ctx->cfg = *cfg;
+  else { ctx->cfg.device = -1; ctx->cfg.kernel = MMF_KERNEL_AUTO; }
+  int dev = ctx->cfg.device;
+  if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+  if (dev >= ndev) { delete ctx; return fail(MMF_E_INVALID, "device %d out of range (%d devices)", dev, ndev); }
+  ctx->device = dev;
+  auto bail = [&](cudaError_t ee, const char* what) {
+    int rc = fail(MMF_E_CUDA, "%s failed: %s", what, cudaGetErrorString(ee));
+    delete ctx;
+    return rc;
+  };
+  if ((e = cudaSetDevice(dev)) != cudaSuccess) return bail(e, "cudaSetDevice");
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
+  ctx->sm_count = prop.multiProcessorCount;
+  if (prop.major != 10) {
+    int rc = fail(MMF_E_UNSUPPORTED, "device %d is sm_%d%d; libmmf is built for sm_100a (B200) only", dev, prop.major,
+                  prop.minor);
+    delete ctx;
+    return rc;
+  }
+  if (ctx->cfg.stream) { ctx->stream = (cudaStream_t)ctx->cfg.stream; ctx->own_stream = false; }
+  else {
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    ctx->own_stream = true;
+  }
+  if ((e = cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+  if ((e = cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+  cudaEventCreate(&ctx->ev_a); cudaEventCreate(&ctx->ev_b); cudaEventCreate(&ctx->ev_k0); cudaEventCreate(&ctx->ev_k1);
+  for (int i = 0; i < NBUF; ++i) {
+    cudaEventCreateWithFlags(&ctx->st[i].ev_h2d, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->st[i].ev_comp, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->st[i].ev_d2h, cudaEventDisableTiming);
+  }
+  if ((e = cudaMalloc(&ctx->d_pending, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
+  cudaMemset(ctx->d_pending, 0, sizeof(uint32_t));
+  *out = ctx;
+  return MMF_OK;
+}
+
+int mmf_destroy(mmf_ctx* ctx) {
+  if (!ctx) return MMF_OK;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  free_plan(ctx->plan);
+  for (int i = 0; i < NBUF; ++i) {
+    Staging& s = ctx->st[i];
+    cudaFree(s.d_y); cudaFree(s.d_out); cudaFree(s.d_beta); cudaFree(s.d_status);
+    if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
+    if (s.ev_comp) cudaEventDestroy(s.ev_comp);
+    if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
+  }
+  cudaFree(ctx->d_pending);
+  cudaFree(ctx->d_status_scratch);
+  if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+  if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+  if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
+  if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+  if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+  delete ctx;
+  return MMF_OK;
+}
+
+int mmf_set_stream(mmf_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return fail(MMF_E_INVALID, "ctx is NULL");
+  if (ctx->own_stream && ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+  ctx->stream = (cudaStream_t)cuda_stream;      // NULL = legacy default stream
+  ctx->own_stream = false;
+  return MMF_OK;
+}
+
+int mmf_synchronize(mmf_ctx* ctx) {
+  if (!ctx) return fail(MMF_E_INVALID, "ctx is NULL");
+  CU_TRY(cudaSetDevice(ctx->device));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->s_h2d));
+  CU_TRY(cudaStreamSynchronize(ctx->s_d2h));
+  return MMF_OK;
+}
+
+int mmf_plan_design(mmf_ctx* ctx, const double* X, int32_t n_rows, int32_t p, int32_t t_fit, int32_t has_constant) {
+  if (!ctx || !X) return fail(MMF_E_INVALID, "ctx or X is NULL");
+  if (p < 1 || p > P) return fail(MMF_E_INVALID, "p=%d outside [1,%d]", p, P);
+  if (t_fit < 1 || n_rows < t_fit) return fail(MMF_E_INVALID, "need 1 <= t_fit <= n_rows (t_fit=%d n_rows=%d)", t_fit, n_rows);
+  for (int64_t i = 0; i < (int64_t)n_rows * p; ++i)
+    if (!std::isfinite(X[i])) return fail(MMF_E_INVALID, "design matrix has a non-finite entry at %lld", (long long)i);
+  if (has_constant)
+    for (int32_t t = 0; t < n_rows; ++t)
+      if (X[(int64_t)t * p] != 1.0) return fail(MMF_E_INVALID, "has_constant=1 but X[%d,0] != 1", t);
+  CU_TRY(cudaSetDevice(ctx->device));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  free_plan(ctx->plan);
+  Plan& pl = ctx->plan;
+
+  // ---- float64 calendar Gram, in-order Cholesky with aliasing (oracle/mmf_oracle.py: whiten)
+  double G[P][P] = {}, L[P][P] = {};
+  for (int32_t t = 0; t < t_fit; ++t) {
+    const double* x = X + (int64_t)t * p;
+    for (int i = 0; i < p; ++i)
+      for (int j = 0; j <= i; ++j) G[i][j] += x[i] * x[j];
+  }
+  for (int i = 0; i < P; ++i)
+    for (int j = 0; j < i; ++j) G[j][i] = G[i][j];
+  bool kept[P] = {};
+  for (int j = 0; j < P; ++j) {
+    double dsum = G[j][j];
+    for (int k = 0; k < j; ++k) dsum -= L[j][k] * L[j][k];
+    if (G[j][j] <= 0.0 || dsum <= MMF_CAL_TOL * G[j][j]) continue;
+    kept[j] = true;
+    L[j][j] = std::sqrt(dsum);
+    for (int i = j + 1; i < P; ++i) {
+      double s = G[i][j];
+      for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
+      L[i][j] = s / L[j][j];
+    }
+  }
+  // W = L^-T restricted to the kept set.  Solve L M = I column by column (M = L^-1), W = M^T.
+  int idx[P], nk = 0;
+  for (int j = 0; j < P; ++j) if (kept[j]) idx[nk++] = j;
+  double M[P][P] = {};
+  for (int c = 0; c < nk; ++c) {
+    for (int r = 0; r < nk; ++r) {
+      double s = (r == c) ? 1.0 : 0.0;
+      for (int k = 0; k < r; ++k) s -= L[idx[r]][idx[k]] * M[k][c];
+      M[r][c] = s / L[idx[r]][idx[r]];
+    }
+  }
+  for (int i = 0; i < P * P; ++i) pl.W[i] = 0.0;
+  for (int a = 0; a < nk; ++a)
+    for (int b = 0; b < nk; ++b) pl.W[idx[a] * P + idx[b]] = M[b][a];
+  pl.kept_mask = 0;
+  for (int j = 0; j < P; ++j) if (kept[j]) pl.kept_mask |= 1u << j;
+
+  pl.n_rows = n_rows;
+  pl.n_rows_pad = (n_rows + 31) & ~31;
+  pl.t_fit = t_fit;
+  pl.t_pad = (t_fit + 31) & ~31;
+  pl.has_constant = has_constant ? 1 : 0;
+
+  // ---- A = X W in the three device layouts
+  std::vector<float> A((size_t)n_rows * P, 0.f);
+  for (int32_t t = 0; t < n_rows; ++t) {
+    const double* x = X + (int64_t)t * p;
+    for (int q = 0; q < P; ++q) {
+      double s = 0.0;
+      for (int i = 0; i < p; ++i) s += x[i] * pl.W[i * P + q];
+      A[(size_t)t * P + q] = (float)s;
+    }
+  }
+  std::vector<float> a4((size_t)4 * pl.n_rows_pad * 4, 0.f);
+  for (int32_t t = 0; t < n_rows; ++t)
+    for (int q = 0; q < P; ++q) a4[(((size_t)(q >> 2) * pl.n_rows_pad) + t) * 4 + (q & 3)] = A[(size_t)t * P + q];
+  std::vector<float> at((size_t)2 * P * pl.t_pad, 0.f);
+  for (int32_t t = 0; t < t_fit; ++t)
+    for (int q = 0; q < P; ++q) {
+      const float v = A[(size_t)t * P + q];
+      uint32_t hb; memcpy(&hb, &v, 4); hb &= 0xFFFFE000u;
+      float hi; memcpy(&hi, &hb, 4);
+      float lo = v - hi;
+      uint32_t lb; memcpy(&lb, &lo, 4); lb &= 0xFFFFE000u; memcpy(&lo, &lb, 4);
+      at[(size_t)q * pl.t_pad + t] = hi;
+      at[(size_t)(P + q) * pl.t_pad + t] = lo;
+    }
+  float w32[P * P];
+  for (int i = 0; i < P * P; ++i) w32[i] = (float)pl.W[i];
+
+  CU_TRY(cudaMalloc(&pl.d_a4, a4.size() * sizeof(float)));
+  CU_TRY(cudaMalloc(&pl.d_at, at.size() * sizeof(float)));
+  CU_TRY(cudaMalloc(&pl.d_apred, A.size() * sizeof(float)));
+  CU_TRY(cudaMalloc(&pl.d_w, sizeof(w32)));
+  CU_TRY(cudaMemcpy(pl.d_a4, a4.data(), a4.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(pl.d_at, at.data(), at.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(pl.d_apred, A.data(), A.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(pl.d_w, w32, sizeof(w32), cudaMemcpyHostToDevice));
+  int rc = encode_2d(pl.tmap_at, pl.d_at, (uint64_t)pl.t_pad, (uint64_t)(2 * P), (uint64_t)pl.t_pad * 4, 32, 2 * P);
+  if (rc != MMF_OK) return rc;
+  pl.valid = true;
+  return MMF_OK;
+}
+
+int mmf_get_whitening(mmf_ctx* ctx, double* W, int32_t* kept) {
+  if (!ctx) return fail(MMF_E_INVALID, "ctx is NULL");
+  if (!ctx->plan.valid) return fail(MMF_E_NOPLAN, "no design planned");
+  if (W) memcpy(W, ctx->plan.W, sizeof(double) * P * P);
+  if (kept) for (int j = 0; j < P; ++j) kept[j] = (ctx->plan.kept_mask >> j) & 1u;
+  return MMF_OK;
+}
+
+int mmf_fit_forecast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, int32_t pred_start, int32_t n_pred,
+                         float* out_pred, int64_t ld_out, float* out_beta, int32_t* out_status, mmf_stats* stats) {
+  if (!ctx) return fail(MMF_E_INVALID, "ctx is NULL");
+  if (!ctx->plan.valid) return fail(MMF_E_NOPLAN, "mmf_plan_design has not been called");
+  const Plan& pl = ctx->plan;
+  if (n < 0) return fail(MMF_E_INVALID, "n < 0");
+  if (n > 0 && (!y || !out_pred)) return fail(MMF_E_INVALID, "y or out_pred is NULL");
+  if (ld_y < pl.t_fit) return fail(MMF_E_INVALID, "ld_y=%lld < t_fit=%d", (long long)ld_y, pl.t_fit);
+  if (n_pred < 1 || pred_start < 0 || (int64_t)pred_start + n_pred > pl.n_rows)
+    return fail(MMF_E_INVALID, "prediction rows [%d,%d) outside the planned design (%d rows)", pred_start,
+                pred_start + n_pred, pl.n_rows);
+  if (ld_out < n_pred) return fail(MMF_E_INVALID, "ld_out=%lld < n_pred=%d", (long long)ld_out, n_pred);
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (n == 0) return MMF_OK;
+  CU_TRY(cudaSetDevice(ctx->device));
+
+  const bool y_dev = is_device_ptr(y), o_dev = is_device_ptr(out_pred);
+  const bool b_dev = out_beta ? is_device_ptr(out_beta) : true;
+  const bool s_dev = out_status ? is_device_ptr(out_status) : true;
+  int launches = 0, kernel_used = 0;
+  int64_t h2d = 0, d2h = 0;
+
+  if (y_dev && o_dev && b_dev && s_dev) {
+    // ------------------------------------------------ all device: just enqueue
+    int32_t* status = out_status;
+    if (!status) {
+      int rc = grow((void**)&ctx->d_status_scratch, &ctx->status_scratch_cap, (size_t)n * sizeof(int32_t));
+      if (rc != MMF_OK) return rc;
+      status = ctx->d_status_scratch;
+    }
+    if (stats) CU_TRY(cudaEventRecord(ctx->ev_k0, ctx->stream));
+    int rc = run_device(ctx, y, n, ld_y, pred_start, n_pred, out_pred, ld_out, out_beta, status, ctx->stream,
+                        &launches, &kernel_used);
+    if (rc != MMF_OK) return rc;
+    if (stats) {
+      CU_TRY(cudaEventRecord(ctx->ev_k1, ctx->stream));
+      CU_TRY(cudaEventSynchronize(ctx->ev_k1));
+      CU_TRY(cudaEventElapsedTime(&stats->kernel_ms, ctx->ev_k0, ctx->ev_k1));
+      stats->total_ms = stats->kernel_ms;
+      uint32_t pend = 0;
+      CU_TRY(cudaMemcpy(&pend, ctx->d_pending, sizeof(pend), cudaMemcpyDeviceToHost));
+      stats->n_pending = (kernel_used == MMF_KERNEL_TC) ? pend : 0;
+    }
+  } else {
+    // ------------------------------------------------ host buffers: pipelined chunks
+    int64_t chunk = ctx->cfg.chunk_series > 0 ? ctx->cfg.chunk_series : 32768;
+    if (chunk > n) chunk = n;
+    const int64_t pitch = (pl.t_fit + 3) & ~3;                 // staged row pitch (floats), TMA-friendly
+    const int64_t opitch = (n_pred + 3) & ~3;
+    for (int i = 0; i < NBUF; ++i) {
+      Staging& s = ctx->st[i];
+      int rc = MMF_OK;
+      if (!y_dev) rc = grow((void**)&s.d_y, &s.y_cap, (size_t)chunk * pitch * sizeof(float));
+      if (rc == MMF_OK && !o_dev) rc = grow((void**)&s.d_out, &s.out_cap, (size_t)chunk * opitch * sizeof(float));
+      if (rc == MMF_OK && out_beta && !b_dev) rc = grow((void**)&s.d_beta, &s.beta_cap, (size_t)chunk * P * sizeof(float));
+      if (rc == MMF_OK && (!out_status || !s_dev)) rc = grow((void**)&s.d_status, &s.status_cap, (size_t)chunk * sizeof(int32_t));
+      if (rc != MMF_OK) return rc;
+    }
+    CU_TRY(cudaEventRecord(ctx->ev_a, ctx->stream));
+    CU_TRY(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_a, 0));
+    CU_TRY(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_a, 0));
+    int it = 0;
+    for (int64_t off = 0; off < n; off += chunk, ++it) {
+      const int64_t m = std::min(chunk, n - off);
+      Staging& s = ctx->st[it % NBUF];
+      const float* yk; int64_t ldk;
+      if (y_dev) { yk = y + off * ld_y; ldk = ld_y; }
+      else {
+        if (it >= NBUF) CU_TRY(cudaStreamWaitEvent(ctx->s_h2d, s.ev_comp, 0));     // staging buffer free again
+        CU_TRY(cudaMemcpy2DAsync(s.d_y, (size_t)pitch * 4, y + off * ld_y, (size_t)ld_y * 4, (size_t)pl.t_fit * 4,
+                                 (size_t)m, cudaMemcpyHostToDevice, ctx->s_h2d));
+        CU_TRY(cudaEventRecord(s.ev_h2d, ctx->s_h2d));
+        CU_TRY(cudaStreamWaitEvent(ctx->stream, s.ev_h2d, 0));
+        yk = s.d_y; ldk = pitch;
+        h2d += m * (int64_t)pl.t_fit * 4;
+      }
+      float* ok = o_dev ? out_pred + off * ld_out : s.d_out;
+      const int64_t ldo = o_dev ? ld_out : opitch;
+      float* bk = out_beta ? (b_dev ? out_beta + off * P : s.d_beta) : nullptr;
+      int32_t* sk = (out_status && s_dev) ? out_status + off : s.d_status;
+      if (it >= NBUF) CU_TRY(cudaStreamWaitEvent(ctx->stream, s.ev_d2h, 0));        // output staging drained
+      int rc = run_device(ctx, yk, m, ldk, pred_start, n_pred, ok, ldo, bk, sk, ctx->stream, &launches, &kernel_used);
+      if (rc != MMF_OK) return rc;
+      CU_TRY(cudaEventRecord(s.ev_comp, ctx->stream));
+      bool any_d2h = false;
+      if (!o_dev) {
+        CU_TRY(cudaStreamWaitEvent(ctx->s_d2h, s.ev_comp, 0));
+        CU_TRY(cudaMemcpy2DAsync(out_pred + off * ld_out, (size_t)ld_out * 4, s.d_out, (size_t)opitch * 4,
+                                 (size_t)n_pred * 4, (size_t)m, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        d2h += m * (int64_t)n_pred * 4; any_d2h = true;
+      }
+      if (out_beta && !b_dev) {
+        if (!any_d2h) CU_TRY(cudaStreamWaitEvent(ctx->s_d2h, s.ev_comp, 0));
+        CU_TRY(cudaMemcpyAsync(out_beta + off * P, s.d_beta, (size_t)m * P * 4, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        d2h += m * (int64_t)P * 4; any_d2h = true;
+      }
+      if (out_status && !s_dev) {
+        if (!any_d2h) CU_TRY(cudaStreamWaitEvent(ctx->s_d2h, s.ev_comp, 0));
+        CU_TRY(cudaMemcpyAsync(out_status + off, s.d_status, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        d2h += m * 4; any_d2h = true;
+      }
+      CU_TRY(cudaEventRecord(s.ev_d2h, ctx->s_d2h));
+    }
+    // join: compute stream waits for the copies, then the host waits for everything
+    CU_TRY(cudaEventRecord(ctx->ev_b, ctx->s_d2h));
+    CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_b, 0));
+    CU_TRY(cudaEventRecord(ctx->ev_b, ctx->stream));
+    CU_TRY(cudaEventSynchronize(ctx->ev_b));
+    if (stats) {
+      CU_TRY(cudaEventElapsedTime(&stats->total_ms, ctx->ev_a, ctx->ev_b));
+      stats->kernel_ms = 0.f;   // kernels overlap the copies here; use a device-pointer call to time them
+    }
+  }
+  if (stats) {
+    stats->n_series = n;
+    stats->h2d_bytes = h2d;
+    stats->d2h_bytes = d2h;
+    stats->kernel_launches = launches;
+    stats->kernel_used = kernel_used;
+  }
+  return MMF_OK;
+}
+
+int mmf_alloc_pinned(size_t bytes, void** out) {
+  if (!out) return fail(MMF_E_INVALID, "out is NULL");
+  CU_TRY(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+  return MMF_OK;
+}
+
+int mmf_free_pinned(void* p) {
+  if (p) CU_TRY(cudaFreeHost(p));
+  return MMF_OK;
+}
+
+int mmf_host_register(void* p, size_t bytes) {
+  if (!p) return fail(MMF_E_INVALID, "pointer is NULL");
+  CU_TRY(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+  return MMF_OK;
+}
+
+int mmf_host_unregister(void* p) {
+  if (p) CU_TRY(cudaHostUnregister(p));
+  return MMF_OK;
+}
+
+}  // extern "C"

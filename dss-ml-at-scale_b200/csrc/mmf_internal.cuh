@@ -1,0 +1,58 @@
+// Internal declarations shared by the C-ABI translation unit and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/mmf.h"
+
+namespace mmf {
+
+constexpr int P = MMF_P;                 // design columns
+constexpr int NPAIR = P * (P + 1) / 2;   // packed symmetric Gram entries (136)
+
+// ---- device-side view of a planned design --------------------------------
+// A = X W (whitened, float32).  Three layouts of the same numbers:
+//  a4   : column-blocked float4, a4[j*n_rows_pad + t] = A[t][4j..4j+3]   (warp kernel: conflict-free LDS.128)
+//  at   : [2P][t_pad] K-major rows for the tensor-core B operand: row n<P is tf32-hi of column n,
+//         row P+n is the tf32 residual (lo); columns t >= t_fit are zero            (tcgen05 kernel)
+//  apred: [n_rows][P] row-major                                                     (tcgen05 epilogue)
+struct DesignView {
+  const float4* a4;
+  const float*  at;
+  const float*  apred;
+  const float*  w;          // [P][P] row-major float32 whitening matrix (beta = W gamma)
+  int32_t n_rows;
+  int32_t n_rows_pad;       // multiple of 32
+  int32_t t_fit;
+  int32_t t_pad;            // t_fit rounded up to 32
+  uint32_t kept_mask;       // bit j set: whitened column j retained on the calendar
+  int32_t has_constant;
+};
+
+struct FitArgs {
+  const float* y;
+  int64_t n;
+  int64_t ld_y;
+  int32_t pred_start;
+  int32_t n_pred;
+  float* out;
+  int64_t ld_out;
+  float* out_beta;          // nullable [n][P]
+  int32_t* status;          // never null inside the library (scratch if caller passed NULL)
+  int32_t only_pending;     // 1: process only rows whose status == MMF_STATUS_PENDING
+  const uint32_t* pending_count;  // nullable; if non-null and *pending_count == 0 the kernel exits at once
+};
+
+// warp-per-series CUDA-core kernel (general path)
+cudaError_t launch_fit_warp(const DesignView& d, const FitArgs& a, int sm_count, cudaStream_t s);
+size_t fit_warp_smem_bytes(const DesignView& d, int* smem_rows);
+
+// TMA + tcgen05/TMEM kernel (fully observed fast path).  `tmap_y` / `tmap_at` are CUtensorMap blobs.
+struct TcLaunch {
+  alignas(64) unsigned char tmap_y[128];
+  alignas(64) unsigned char tmap_at[128];
+};
+cudaError_t launch_fit_tc(const DesignView& d, const FitArgs& a, const TcLaunch& tl,
+                          uint32_t* pending_count, int sm_count, cudaStream_t s);
+bool fit_tc_supported(const DesignView& d, const FitArgs& a, const char** why);
+
+}  // namespace mmf

@@ -1,0 +1,222 @@
+"""``ForecastEngine`` -- the Python face of one ``mmf_ctx`` (one per process / per GPU).
+
+Replaces, for every group at once, what one Spark Python worker does per group in
+``build_tune_and_score_model`` (group_apply/02_Fine_Grained_Demand_Forecasting.py:
+435-494): fit on the train rows, predict the requested rows.  Inputs are packed
+series ``y[N, ld]`` float32 (NaN = missing) that share one calendar.
+
+Buffers may be NumPy arrays (host; pinned ones from :func:`pinned_empty` copy at
+PCIe speed) or CUDA ``torch`` tensors (device; zero copies).  PyTorch is only
+plumbing here (device memory / streams); all arithmetic is in ``libmmf.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _native as N
+from . import design as D
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _describe(x, name: str):
+    """-> (ptr, rows, cols, ld) of a 1-D/2-D float32/int32 buffer with unit inner stride."""
+    if _is_torch(x):
+        if x.dim() == 1:
+            return x.data_ptr(), x.shape[0], 1, 1
+        if x.dim() != 2 or (x.shape[1] > 1 and x.stride(1) != 1):
+            raise ValueError(f"{name}: need a 2-D tensor with unit inner stride")
+        return x.data_ptr(), x.shape[0], x.shape[1], x.stride(0)
+    a = x
+    if not isinstance(a, np.ndarray):
+        raise TypeError(f"{name}: expected numpy.ndarray or torch.Tensor, got {type(x)}")
+    if a.ndim == 1:
+        return a.ctypes.data, a.shape[0], 1, 1
+    if a.ndim != 2 or (a.shape[1] > 1 and a.strides[1] != a.itemsize):
+        raise ValueError(f"{name}: need a 2-D array with unit inner stride")
+    if a.strides[0] % a.itemsize:
+        raise ValueError(f"{name}: row stride is not a multiple of the item size")
+    return a.ctypes.data, a.shape[0], a.shape[1], a.strides[0] // a.itemsize
+
+
+def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
+    """NumPy array over page-locked host memory (``mmf_alloc_pinned``): the Arrow/NumPy ->
+    device hop becomes one ``cudaMemcpyAsync`` per chunk."""
+    lib = N.load()
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    p = C.c_void_p()
+    N.check(lib.mmf_alloc_pinned(max(nbytes, 1), C.byref(p)))
+    buf = (C.c_byte * max(nbytes, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    weakref.finalize(buf, lib.mmf_free_pinned, p.value)
+    return arr
+
+
+def alloc_packed(n: int, t: int, pinned: bool = True):
+    """Host buffer for ``n`` packed series of length ``t`` with a TMA-friendly row pitch
+    (multiple of 4 floats).  Returns the [n, t] view; ``view.base`` keeps the padded rows."""
+    ld = (t + 3) & ~3
+    full = pinned_empty((n, ld)) if pinned else np.empty((n, ld), dtype=np.float32)
+    return full[:, :t]
+
+
+@dataclass
+class Stats:
+    kernel_ms: float
+    total_ms: float
+    n_series: int
+    n_pending: int
+    h2d_bytes: int
+    d2h_bytes: int
+    kernel_launches: int
+    kernel_used: str
+
+
+class ForecastEngine:
+    """One library context: streams, staging buffers, the planned calendar design."""
+
+    def __init__(self, device: int | None = None, kernel: str = "auto", assume_finite: bool = False,
+                 chunk_series: int = 0, stream: int | None = None):
+        self._lib = N.load()
+        cfg = N.MmfConfig()
+        cfg.device = -1 if device is None else int(device)
+        cfg.kernel = N.KERNELS[kernel]
+        cfg.assume_finite = 1 if assume_finite else 0
+        cfg.chunk_series = int(chunk_series)
+        cfg.stream = stream
+        h = C.c_void_p()
+        N.check(self._lib.mmf_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        self._finalizer = weakref.finalize(self, self._lib.mmf_destroy, h)
+        self.t_fit = None
+        self.n_rows = None
+        self.launches = 0            # kernels launched through this engine (bench reports it)
+
+    # ---- lifecycle -----------------------------------------------------------
+    def close(self) -> None:
+        if self._finalizer.alive:
+            self._finalizer()
+
+    def set_stream(self, cuda_stream_ptr: int | None) -> None:
+        """Enqueue on a caller-owned stream (e.g. ``torch.cuda.current_stream().cuda_stream``)."""
+        N.check(self._lib.mmf_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def synchronize(self) -> None:
+        N.check(self._lib.mmf_synchronize(self._h))
+
+    # ---- design --------------------------------------------------------------
+    def plan(self, X: np.ndarray, t_fit: int, has_constant: bool) -> None:
+        """Plan a raw design ``X[n_rows, p<=16]`` (float64): rows [0,t_fit) fit, the rest forecast."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        if X.ndim != 2:
+            raise ValueError("X must be 2-D")
+        N.check(self._lib.mmf_plan_design(self._h, X.ctypes.data, X.shape[0], X.shape[1], int(t_fit),
+                                          1 if has_constant else 0))
+        self.t_fit = int(t_fit)
+        self.n_rows = int(X.shape[0])
+
+    def plan_calendar(self, start, t_len: int, freq: str = "D", horizon: int = 28, mode: str = "future",
+                      design: str = "trend_season_exog"):
+        """Build and plan the design for a bucket of series that start at ``start`` and have
+        ``t_len`` grid rows.  Returns ``(dates_of_prediction_rows, pred_start, n_pred)``."""
+        if mode == "holdout":                       # reference semantics, 02:372-380 + 484-488
+            t_fit = t_len - horizon
+            if t_fit < 1:
+                raise ValueError("series shorter than the forecast horizon")
+            days = D.calendar_grid(start, t_len, freq)
+            pred_start, n_pred = 0, t_len
+        elif mode == "future":
+            t_fit = t_len
+            days = D.calendar_grid(start, t_len + horizon, freq)
+            pred_start, n_pred = t_len, horizon
+        else:
+            raise ValueError(f"mode must be 'holdout' or 'future', got {mode!r}")
+        X = D.design_matrix(days, t_fit, design)
+        self.plan(X, t_fit, D.design_has_constant(design))
+        return days[pred_start:pred_start + n_pred], pred_start, n_pred
+
+    def whitening(self):
+        W = np.zeros((N.MMF_P, N.MMF_P), dtype=np.float64)
+        kept = np.zeros(N.MMF_P, dtype=np.int32)
+        N.check(self._lib.mmf_get_whitening(self._h, W.ctypes.data, kept.ctypes.data))
+        return W, kept.astype(bool)
+
+    # ---- the hot path --------------------------------------------------------
+    def fit_forecast(self, y, pred_start: int, n_pred: int, out=None, beta=None, status=None,
+                     want_beta: bool = False, want_status: bool = False, want_stats: bool = False):
+        """Fit every row of ``y`` on the planned design and evaluate rows
+        [pred_start, pred_start+n_pred).  Returns ``out`` or a dict when extras are requested."""
+        if self.t_fit is None:
+            raise RuntimeError("plan()/plan_calendar() must be called first")
+        yp, n, t_have, ld_y = _describe(y, "y")
+        if t_have < self.t_fit:
+            raise ValueError(f"y has {t_have} columns, the plan needs t_fit={self.t_fit}")
+        on_dev = _is_torch(y) and y.is_cuda
+        if _is_torch(y):
+            import torch
+            if y.dtype != torch.float32:
+                raise TypeError("y must be float32")
+        elif y.dtype != np.float32:
+            raise TypeError("y must be float32")
+
+        def make(shape, np_dtype):
+            if on_dev:
+                import torch
+                return torch.empty(shape, device=y.device,
+                                   dtype=torch.float32 if np_dtype == np.float32 else torch.int32)
+            return np.empty(shape, dtype=np_dtype)
+
+        if out is None:
+            out = make((n, n_pred), np.float32)
+        if want_beta and beta is None:
+            beta = make((n, N.MMF_P), np.float32)
+        if want_status and status is None:
+            status = make((n,), np.int32)
+        op, on, ocols, ld_out = _describe(out, "out")
+        if on != n or ocols < n_pred:
+            raise ValueError("out has the wrong shape")
+        bp = _describe(beta, "beta")[0] if beta is not None else None
+        sp = _describe(status, "status")[0] if status is not None else None
+        st = N.MmfStats() if want_stats else None
+        N.check(self._lib.mmf_fit_forecast_f32(self._h, yp, n, ld_y, int(pred_start), int(n_pred), op, ld_out,
+                                               bp, sp, C.byref(st) if st is not None else None))
+        if not (want_beta or want_status or want_stats):
+            return out
+        res = {"pred": out}
+        if beta is not None:
+            res["beta"] = beta
+        if status is not None:
+            res["status"] = status
+        if st is not None:
+            self.launches += st.kernel_launches
+            res["stats"] = Stats(st.kernel_ms, st.total_ms, st.n_series, st.n_pending, st.h2d_bytes,
+                                 st.d2h_bytes, st.kernel_launches,
+                                 {N.KERNEL_WARP: "warp", N.KERNEL_TC: "tc"}.get(st.kernel_used, "?"))
+        return res
+
+
+_default_engine: ForecastEngine | None = None
+
+
+def default_engine() -> ForecastEngine:
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = ForecastEngine()
+    return _default_engine
+
+
+def forecast_packed(y, start, freq: str = "D", horizon: int = 28, mode: str = "future",
+                    design: str = "trend_season_exog", engine: ForecastEngine | None = None, **kw):
+    """``y[N,T]`` on one shared calendar -> predictions ``[N, horizon]`` (future) or ``[N, T]``
+    (holdout: fitted values for the train dates + forecast for the held-out dates)."""
+    eng = engine or default_engine()
+    t_len = y.shape[1]
+    _, pred_start, n_pred = eng.plan_calendar(start, t_len, freq, horizon, mode, design)
+    return eng.fit_forecast(y, pred_start, n_pred, **kw)

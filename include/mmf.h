@@ -1,0 +1,131 @@
+/*
+ * mmf.h -- C ABI of libmmf.so, the B200-native many-models fit+forecast engine.
+ *
+ * This is the drop-in boundary for ONE hot path of sebrahimi1988/dss-ml-at-scale:
+ * the per-(Product,SKU) fit + predict that the reference fans out with
+ *     enriched_df.repartition(n_tasks,"Product","SKU").groupBy("Product","SKU")
+ *                .applyInPandas(build_tune_and_score_model, schema=tuning_schema)
+ * (group_apply/02_Fine_Grained_Demand_Forecasting.py:523-528, UDF body 417-494).
+ * The reference has no FFI of its own (it is pure Python on Spark); the binding a
+ * maintainer adds is the ctypes stub in INTEGRATION.md.  Every entry point below
+ * names the reference lines it replaces.
+ *
+ * Conventions
+ *  - plain C, no CUDA/torch types: device and host pointers are both `float*`;
+ *    the library classifies them with cudaPointerGetAttributes.
+ *  - every function returns 0 on success or a negative MMF_E_* code; the text is
+ *    available from mmf_last_error() (thread local).  Nothing throws across the ABI.
+ *  - per-series numerical outcomes go to `out_status`, never to the return code.
+ *  - a ctx is single-caller; separate ctxs (one per process / per GPU) are
+ *    independent.  Missing observations are NaN (any non-finite value) in `y`.
+ *  - series are rows: y[i*ld_y + t], t = 0..t_fit-1 on the shared regular grid
+ *    (the packed form of `sort_values("Date").set_index("Date").asfreq(freq)`,
+ *    reference 02:422-423).
+ */
+#ifndef MMF_H_
+#define MMF_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMF_VERSION 100          /* 0.1.0 */
+#define MMF_P 16                 /* design columns (zero-pad narrower designs) */
+#define MMF_PIVOT_TOL 1e-3f      /* per-series relative Cholesky pivot threshold */
+#define MMF_CAL_TOL 1e-10        /* aliasing threshold on the float64 calendar Gram */
+
+/* return codes */
+#define MMF_OK 0
+#define MMF_E_INVALID (-1)
+#define MMF_E_CUDA (-2)
+#define MMF_E_UNSUPPORTED (-3)
+#define MMF_E_NOPLAN (-4)
+#define MMF_E_NOMEM (-5)
+
+/* per-series status (out_status) */
+#define MMF_STATUS_OK 0          /* fit on all requested rows */
+#define MMF_STATUS_EMPTY 1       /* no observed fit row: outputs are NaN */
+#define MMF_STATUS_RANKDEF 2     /* ok, but a whitened column was dropped for this series' mask */
+#define MMF_STATUS_PENDING (-1)  /* internal: fast path saw a non-finite value, masked pass owes a result */
+
+/* kernel selection */
+#define MMF_KERNEL_AUTO 0        /* tcgen05 fast path + masked fix-up where eligible, else warp kernel */
+#define MMF_KERNEL_WARP 1        /* warp-per-series CUDA-core kernel (general: masks, any ld, any n_pred) */
+#define MMF_KERNEL_TC 2          /* TMA + tcgen05/TMEM kernel (fully observed rows; others -> masked pass) */
+
+typedef struct mmf_ctx mmf_ctx;
+
+typedef struct mmf_config {
+  int32_t device;          /* CUDA device ordinal, -1 = current device */
+  int32_t kernel;          /* MMF_KERNEL_* */
+  int32_t assume_finite;   /* 1: caller guarantees y has no NaN/Inf, skip the masked fix-up pass */
+  int32_t reserved0;
+  int64_t chunk_series;    /* host-buffer path: series per pipelined chunk (0 = library default) */
+  void*   stream;          /* cudaStream_t to enqueue on (NULL = library-owned stream) */
+} mmf_config;
+
+typedef struct mmf_stats {
+  float   kernel_ms;       /* device time of the fit kernels (CUDA events) */
+  float   total_ms;        /* device time of the whole call incl. copies */
+  int64_t n_series;
+  int64_t n_pending;       /* rows the fast path handed to the masked pass */
+  int64_t h2d_bytes;
+  int64_t d2h_bytes;
+  int32_t kernel_launches; /* kernels of this library launched by the call */
+  int32_t kernel_used;     /* MMF_KERNEL_WARP or MMF_KERNEL_TC (dominant kernel) */
+} mmf_stats;
+
+/* ---- lifecycle ---------------------------------------------------------- */
+int mmf_version(void);
+const char* mmf_last_error(void);
+int mmf_device_count(int32_t* count);
+/* replaces: the Spark Python worker that hosts the UDF (one ctx per worker process) */
+int mmf_create(const mmf_config* cfg, mmf_ctx** out);
+int mmf_destroy(mmf_ctx* ctx);
+int mmf_set_stream(mmf_ctx* ctx, void* cuda_stream);   /* borrow e.g. torch's current stream */
+int mmf_synchronize(mmf_ctx* ctx);
+
+/* ---- design plan --------------------------------------------------------
+ * X: [n_rows, p] row-major float64 design rows on the shared calendar; rows
+ * [0,t_fit) are the fit window, later rows are forecast rows.  p <= MMF_P.
+ * has_constant: 1 iff X[:,0] == 1 for every row (enables per-series centring).
+ * The library whitens the calendar Gram in float64 (in-order Cholesky, aliased
+ * columns dropped), uploads A = X W in the layouts the kernels use.
+ * replaces: the design the reference builds per row in add_exo_variables
+ * (02:343-358) and hands to SARIMAX as exog= (02:441-449, 472-480).           */
+int mmf_plan_design(mmf_ctx* ctx, const double* X, int32_t n_rows, int32_t p,
+                    int32_t t_fit, int32_t has_constant);
+/* W [MMF_P*MMF_P] row-major (beta = W gamma), kept[MMF_P] 0/1; either may be NULL */
+int mmf_get_whitening(mmf_ctx* ctx, double* W, int32_t* kept);
+
+/* ---- the hot path -------------------------------------------------------
+ * Fit every series on rows [0,t_fit) of the planned design and evaluate rows
+ * [pred_start, pred_start+n_pred):
+ *   holdout / drop-in mode : pred_start = 0,     n_pred = T      (Demand_Fitted for every date)
+ *   future mode            : pred_start = t_fit, n_pred = horizon
+ * y        [n, ld_y]   float32, host or device, NaN = missing
+ * out_pred [n, ld_out] float32, host or device (same side as y not required)
+ * out_beta [n, MMF_P]  nullable: coefficients on the raw X columns
+ * out_status [n]       nullable
+ * Device-pointer calls are enqueued on the ctx stream and return without
+ * synchronising unless `stats` is non-NULL.  Host-pointer calls pipeline
+ * H2D / kernel / D2H in chunks and return when the results are in host memory.
+ * replaces: model.fit + predict + output assembly of build_tune_and_score_model
+ * (02:435-494) for ALL groups of the applyInPandas fan-out (02:523-528).      */
+int mmf_fit_forecast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y,
+                         int32_t pred_start, int32_t n_pred,
+                         float* out_pred, int64_t ld_out,
+                         float* out_beta, int32_t* out_status, mmf_stats* stats);
+
+/* ---- host memory helpers (Arrow buffers -> one cudaMemcpyAsync) ---------- */
+int mmf_alloc_pinned(size_t bytes, void** out);
+int mmf_free_pinned(void* p);
+int mmf_host_register(void* p, size_t bytes);     /* pin an existing (Arrow/NumPy) buffer */
+int mmf_host_unregister(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMF_H_ */

@@ -1,0 +1,185 @@
+"""CPU: the oracle against the reference-executed fixtures, the frozen golden vectors,
+an independent lstsq route and closed-form known-answer tests."""
+import datetime as dt
+
+import numpy as np
+import pytest
+
+import mmf
+from oracle import mmf_oracle as O
+
+
+# ---- pinned against the reference's own code (tests/golden/make_reference_fixtures.py) -----
+@pytest.mark.parametrize("name", ["weekly", "daily"])
+def test_exo_variables_match_reference_code(reference_fixtures, name):
+    days = reference_fixtures[f"exo_{name}_days"].astype("datetime64[D]")
+    want = reference_fixtures[f"exo_{name}"]
+    got_oracle = O.exo_variables([dt.date.fromisoformat(str(d)) for d in days])
+    got_pkg = mmf.design.exo_variables(days)
+    assert np.array_equal(got_oracle, want)            # 0/1 floats: bit exact
+    assert np.array_equal(got_pkg, want)
+
+
+def test_exo_counts_on_reference_calendar(reference_fixtures):
+    # covid 73 / christmas 6 / new_year 12 ones on the 157-week calendar
+    assert reference_fixtures["exo_weekly"].sum(axis=0).tolist() == [73.0, 6.0, 12.0]
+
+
+def test_split_matches_reference_code(reference_fixtures):
+    for n, h, n_train, n_score, first_score, last_train in reference_fixtures["split_cases"]:
+        data = np.arange(n)
+        for split in (O.split_train_score_data, mmf.split_train_score_data):
+            tr, sc = split(data, int(h))
+            assert (len(tr), len(sc)) == (n_train, n_score)
+            assert sc[0] == first_score and tr[-1] == last_train
+
+
+def test_generator_calendar_matches_reference_code(reference_fixtures):
+    days, helper, corona, xmas = mmf.synth.reference_calendar()
+    assert np.array_equal(days.astype(np.int64), reference_fixtures["gen_days"])
+    assert np.array_equal(helper, reference_fixtures["gen_helper"])
+    assert np.allclose(corona, reference_fixtures["gen_corona_factor"], rtol=0, atol=1e-15)
+    assert np.array_equal(xmas, reference_fixtures["gen_factor_xmas"])
+    assert np.array_equal(mmf.design.iso_week(days), reference_fixtures["gen_week"])
+
+
+# ---- frozen oracle outputs -------------------------------------------------------------------
+def test_oracle_reproduces_golden(oracle_golden):
+    g = oracle_golden
+    y = g["ref_weekly_y"]
+    T = y.shape[1]
+    grid = O.calendar_grid(g["ref_weekly_start"][0].astype("datetime64[D]"), T, "W-MON")
+    pred, status = O.fit_forecast_packed(y, O.design_matrix(grid, T - 40), T - 40, 0, T)
+    assert np.allclose(pred, g["ref_weekly_fitted"], rtol=0, atol=1e-7)
+    assert np.array_equal(status, g["ref_weekly_status"])
+
+    y = g["daily365_y"]
+    grid = O.calendar_grid(g["daily365_start"][0].astype("datetime64[D]"), 365 + 28, "D")
+    pred, status = O.fit_forecast_packed(y, O.design_matrix(grid, 365), 365, 365, 28)
+    assert np.allclose(pred, g["daily365_pred"], rtol=0, atol=1e-7)
+    assert np.array_equal(status, g["daily365_status"])
+
+
+def test_package_design_equals_oracle_design():
+    for freq, n, t_fit, start in (("D", 1123, 1095, "2018-07-21"), ("W-MON", 157, 117, "2018-07-23"),
+                                  ("D", 400, 365, "2019-12-20")):
+        days = mmf.design.calendar_grid(start, n, freq)
+        got = mmf.design.design_matrix(days, t_fit)
+        want = O.design_matrix(O.calendar_grid(dt.date.fromisoformat(start), n, freq), t_fit)
+        assert np.abs(got - want).max() < 1e-12
+        got = mmf.design.design_matrix(days, t_fit, "exog_only")
+        want = O.design_matrix(O.calendar_grid(dt.date.fromisoformat(start), n, freq), t_fit, "exog_only")
+        assert np.array_equal(got, want)
+
+
+# ---- the whitened-Cholesky route against an independent solver ----------------------------
+def test_whitened_route_equals_lstsq(oracle_golden):
+    y = oracle_golden["daily1095_y"].astype(np.float64)
+    grid = O.calendar_grid(oracle_golden["daily1095_start"][0].astype("datetime64[D]"), 1095 + 28, "D")
+    X = O.design_matrix(grid, 1095)
+    pred, status = O.fit_forecast_packed(y, X, 1095, 1095, 28)
+    assert (status == 0).all()
+    for i in range(0, y.shape[0], 5):
+        ref = O.lstsq_reference(y[i], X[:1095], X[1095:])
+        assert np.abs(pred[i] - ref).max() < 1e-6
+    # with gaps
+    rng = np.random.default_rng(0)
+    yi = y[3].copy()
+    yi[rng.random(1095) < 0.1] = np.nan
+    p1, st = O.fit_forecast_packed(yi[None], X, 1095, 0, 1123)
+    assert st[0] == 0
+    assert np.abs(p1[0] - O.lstsq_reference(yi, X[:1095], X)).max() < 1e-6
+
+
+def test_whiten_is_orthonormal_and_drops_aliased():
+    grid = O.calendar_grid(dt.date(2020, 7, 20), 365 + 28, "D")     # covid == 1 everywhere
+    X = O.design_matrix(grid, 365)
+    W, kept = O.whiten(X[:365])
+    assert not kept[13] and kept.sum() == 15
+    A = X[:365] @ W
+    G = A.T @ A
+    assert np.abs(G - np.diag(kept.astype(float))).max() < 1e-9
+    # weekly grid: every date is a Monday -> the six day-of-week dummies vanish
+    Xw = O.design_matrix(O.calendar_grid(dt.date(2018, 7, 23), 157, "W-MON"), 117)
+    _, keptw = O.whiten(Xw[:117])
+    assert not keptw[3:9].any() and keptw[[0, 1, 2, 9, 10, 11, 12, 13, 14, 15]].all()
+
+
+# ---- closed-form known answers ------------------------------------------------------------------
+def _daily_design(T=200, H=28, start=dt.date(2019, 1, 1)):
+    grid = O.calendar_grid(start, T + H, "D")
+    return O.design_matrix(grid, T)
+
+
+def test_kat_pure_line_forecast_is_exact():
+    X = _daily_design()
+    t = np.arange(228, dtype=np.float64)
+    y = 500.0 + 3.0 * t
+    pred, st = O.fit_forecast_packed(y[None, :200], X, 200, 200, 28)
+    assert st[0] == 0 and np.abs(pred[0] - y[200:]).max() < 1e-6
+
+
+def test_kat_constant_and_weekday_pattern():
+    X = _daily_design()
+    pred, _ = O.fit_forecast_packed(np.full((1, 200), 42.0), X, 200, 200, 28)
+    assert np.abs(pred - 42.0).max() < 1e-7
+    grid = O.calendar_grid(dt.date(2019, 1, 1), 228, "D")
+    pattern = np.array([10.0, 20, 30, 40, 50, 60, 70])
+    y = np.array([pattern[d.weekday()] for d in grid])
+    pred, _ = O.fit_forecast_packed(y[None, :200], X, 200, 200, 28)
+    assert np.abs(pred[0] - y[200:]).max() < 1e-6
+
+
+def test_kat_gaps_empty_and_rank_deficient():
+    X = _daily_design()
+    t = np.arange(228, dtype=np.float64)
+    y = 100.0 + 2.0 * t
+    yg = y[:200].copy()
+    yg[[3, 50, 51, 52, 199]] = np.nan
+    pred, st = O.fit_forecast_packed(yg[None], X, 200, 200, 28)
+    assert st[0] == 0 and np.abs(pred[0] - y[200:]).max() < 1e-6
+    # all missing
+    pred, st = O.fit_forecast_packed(np.full((1, 200), np.nan), X, 200, 200, 28)
+    assert st[0] == 1 and np.isnan(pred).all()
+    # a single observation: everything but the intercept is aliased, forecast == that value
+    y1 = np.full(200, np.nan)
+    y1[17] = 7.5
+    pred, st = O.fit_forecast_packed(y1[None], X, 200, 200, 28)
+    assert st[0] == 2 and np.abs(pred - 7.5).max() < 1e-9
+    # Inf counts as missing
+    yi = y[:200].copy()
+    yi[10] = np.inf
+    pred, st = O.fit_forecast_packed(yi[None], X, 200, 200, 28)
+    assert np.abs(pred[0] - y[200:]).max() < 1e-6
+
+
+def test_exog_only_design_is_ols_on_the_three_dummies():
+    # the literal p=d=q=0 corner of the reference's search space: y ~ covid + christmas + new_year, no constant
+    grid = O.calendar_grid(dt.date(2018, 7, 23), 157, "W-MON")
+    X = O.design_matrix(grid, 117, "exog_only")
+    rng = np.random.default_rng(1)
+    y = 3.0 * X[:, 0] - 2.0 * X[:, 1] + 5.0 * X[:, 2] + rng.normal(0, 0.1, 157)
+    pred, st = O.fit_forecast_packed(y[None, :117], X, 117, 0, 157)
+    beta, *_ = np.linalg.lstsq(X[:117, :3], y[:117], rcond=None)
+    assert np.abs(pred[0] - X[:, :3] @ beta).max() < 1e-9
+
+
+# ---- the per-group UDF skeleton (02:417-494) ---------------------------------------------------
+def test_udf_contract_on_reference_data():
+    df = mmf.synth.reference_weekly_demand(n_skus=2)
+    assert len(df) == 5 * 2 * 157
+    one = df[df["SKU"] == df["SKU"].iloc[0]].sample(frac=1.0, random_state=0)    # shuffled rows, 02:422 sorts
+    out = O.build_tune_and_score_model(one)
+    assert list(out.columns) == ["Product", "SKU", "Date", "Demand", "Demand_Fitted"]
+    assert len(out) == 157 and out["Date"].is_monotonic_increasing
+    assert out["Demand"].dtype == np.float32 and out["Demand_Fitted"].dtype == np.float32
+    # a gap in the input becomes a NaN Demand row on the regular grid (asfreq, 02:423)
+    holed = one[one["Date"] != sorted(one["Date"])[10]]
+    out2 = O.build_tune_and_score_model(holed)
+    assert len(out2) == 157 and np.isnan(out2["Demand"].iloc[10]) and np.isfinite(out2["Demand_Fitted"].iloc[10])
+    allg = O.fanout_apply(df, O.build_tune_and_score_model, ("Product", "SKU"))
+    assert len(allg) == len(df)
+    # future mode
+    fut = O.build_tune_and_score_model(one, mode="future", horizon=8)
+    assert len(fut) == 8 and fut["Demand"].isna().all()
+    assert fut["Date"].iloc[0] == dt.date(2021, 7, 26)
