@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- series fitted+forecast per second on N B200s (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference-shaped CPU fan-out on the host cores
+
+A "step" is one pass of the hot path over one batch of synthetic series:
+  value : device-resident y[N,T] -> forecast table, kernels + (N>1) one NCCL all_gather, timed with
+          CUDA events on the launching stream, max over ranks.
+  e2e   : the same call with HOST (pinned) buffers through the C ABI: H2D of y and D2H of the
+          forecasts are inside the timed region.
+One JSON line on stdout (rank 0).  See DESIGN.md section 5 for how each field is measured.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "series fitted+forecast/sec"
+UNIT = "series/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--series", type=int, default=1_000_000, help="series per GPU (weak scaling)")
+    ap.add_argument("--t", type=int, default=1095)
+    ap.add_argument("--horizon", type=int, default=28)
+    ap.add_argument("--kernel", default="auto", choices=["auto", "warp", "tc"])
+    ap.add_argument("--nan-frac", type=float, default=0.0)
+    ap.add_argument("--e2e-series", type=int, default=0, help="series per e2e step (0 = same as --series)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-groups", type=int, default=0, help="groups per step of the reference arm (0 = 16 x cores)")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for ts, r in self.rows if t0 - 0.05 <= ts <= t1 + 0.15 and len(r) >= 9] or [r for _, r in self.rows if len(r) >= 9]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = [float(r[1]) for r in rows]
+        reasons = set()
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons),
+                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+
+
+# =========================================================================================
+def cpu_port_baseline(y_sample, start, t, h):
+    """The float64 oracle (vectorised packed route; NumPy/OpenBLAS threads) on a bounded sample."""
+    import numpy as np
+    from oracle import mmf_oracle as O
+
+    grid = O.calendar_grid(start, t + h, "D")
+    X = O.design_matrix(grid, t)
+    O.fit_forecast_packed(y_sample[:256], X, t, t, h)                 # warm
+    t0 = time.perf_counter()
+    done = 0
+    budget, block = 12.0, 20000
+    while done < y_sample.shape[0] and time.perf_counter() - t0 < budget:
+        O.fit_forecast_packed(y_sample[done:done + block], X, t, t, h)
+        done += min(block, y_sample.shape[0] - done)
+    dt = time.perf_counter() - t0
+    cores = len(os.sched_getaffinity(0))
+    return {"value": done / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{done} series x {t} days, float64 NumPy oracle (vectorised packed route, BLAS threads), {dt:.1f} s"}
+
+
+_REF = {}
+
+
+def _ref_init(t, h):
+    from oracle import mmf_oracle as O
+    _REF["O"], _REF["t"], _REF["h"] = O, t, h
+
+
+def _ref_one(args):
+    """One Spark-task-shaped unit (reference 02:523-528 + 417-494): a group's rows arrive as an Arrow
+    RecordBatch, become a pandas frame, go through the per-group UDF, and return as Arrow."""
+    import pandas as pd
+    import pyarrow as pa
+    key, dates, vals = args
+    O = _REF["O"]
+    pdf = pd.DataFrame({"Product": key[0], "SKU": key[1], "Date": dates, "Demand": vals})
+    batch = pa.RecordBatch.from_pandas(pdf, preserve_index=False)          # JVM -> Python worker hop
+    out = O.build_tune_and_score_model(batch.to_pandas(), freq="D", horizon=_REF["h"], mode="future")
+    return pa.RecordBatch.from_pandas(out, preserve_index=False).num_rows  # Python worker -> JVM hop
+
+
+def run_reference(args):
+    """--impl reference: the reference-shaped CPU fan-out (one Python UDF call per group, Arrow hop both
+    ways, all host cores), the stand-in for Spark local[*] which needs a JVM + pyspark (absent)."""
+    import multiprocessing as mp
+    import numpy as np
+    import mmf
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    g = args.ref_groups or 16 * cores
+    t, h = args.t, args.horizon
+    y, start = mmf.synth.daily_store_item_demand(g, t, seed=1234)
+    days = mmf.design.calendar_grid(start, t, "D")
+    import datetime as dt
+    dates = [dt.date.fromisoformat(str(d)) for d in days]
+    work = [((f"store{i // 50}", f"item{i}"), dates, y[i]) for i in range(g)]
+    with mp.get_context("fork").Pool(cores, initializer=_ref_init, initargs=(t, h)) as pool:
+        for _ in range(max(args.warmup, 1)):
+            pool.map(_ref_one, work[:cores * 2], chunksize=1)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            rows = pool.map(_ref_one, work, chunksize=1)
+        dtot = time.perf_counter() - t0
+    assert all(r == h for r in rows)
+    value = g * args.steps / dtot
+    sample = (f"{g} groups x {t} days per step, one oracle-UDF call per group with an Arrow RecordBatch round trip, "
+              f"multiprocessing.Pool({cores}); reference SARIMAX+hyperopt UDF itself cannot run here (no statsmodels/"
+              f"hyperopt/pyspark/JVM)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dtot / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{g} (store,item) groups x {t} days per step, {h}-day horizon, future mode "
+                                   f"(bounded sample of the 1M-series workload)", "groups_per_step": g, "t": t,
+                       "horizon": h, "parallelism": f"cpu fan-out x{cores}"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# =========================================================================================
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import mmf
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and rank == 0:
+        print(f"# note: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n, t, h = args.series, args.t, args.horizon
+    K, W = args.steps, max(args.warmup, 3)
+
+    # ---- inputs: resident in HBM before the timed region; 4.4 GB per pass >> 126 MB L2
+    y, start = mmf.synth.daily_store_item_demand_torch(n, t, seed=1234 + rank, nan_frac=args.nan_frac, device=dev)
+    torch.cuda.synchronize()
+    table = torch.zeros((world * n, h), dtype=torch.float32, device=dev)        # the all-gathered forecast table
+    mine = table[rank * n:(rank + 1) * n]
+
+    eng = mmf.ForecastEngine(device=local, kernel=args.kernel)
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)                     # CUDA events below see the kernels
+    _, ps, npred = eng.plan_calendar(start, t, "D", h, "future")
+    st = eng.fit_forecast(y, ps, npred, out=mine, want_stats=True)["stats"]
+    launches_per_call, kernel_used = st.kernel_launches, st.kernel_used
+
+    def step():
+        eng.fit_forecast(y, ps, npred, out=mine)
+        if world > 1:
+            dist.all_gather_into_tensor(table, mine)                            # in-place: mine is table's slice
+
+    for _ in range(W):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K + 2)]
+    wall0 = time.time()
+    ev[0].record()
+    for i in range(K):
+        ev[2 + 2 * i].record()
+        eng.fit_forecast(y, ps, npred, out=mine)
+        ev[3 + 2 * i].record()
+        if world > 1:
+            dist.all_gather_into_tensor(table, mine)
+    ev[1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    wall1 = time.time()
+    total_ms = ev[0].elapsed_time(ev[1])
+    kern_ms = [ev[2 + 2 * i].elapsed_time(ev[3 + 2 * i]) for i in range(K)]
+    tt = torch.tensor([total_ms, sum(kern_ms) / K], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms, kern_ms_avg = float(tt[0]), float(tt[1])
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
+    value = world * n * K / (total_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (algorithmic bytes: 4*T read + 4*H written per series)
+    peak, peak_src = peaks()
+    bytes_per_series = 4 * t + 4 * h
+    achieved = n * bytes_per_series / (kern_ms_avg * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "fit_tc_kernel" if kernel_used == "tc" else "fit_warp_kernel",
+                "peak_source": peak_src, "bytes_per_series": bytes_per_series,
+                "kernel_ms": kern_ms_avg,
+                "note": "CUDA events around each step's libmmf launches in the timed region, max over ranks"}
+
+    # ---- e2e: host (pinned) buffers through the C ABI, H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        ne = args.e2e_series or n
+        eng2 = mmf.ForecastEngine(device=local, kernel=args.kernel)
+        eng2.plan_calendar(start, t, "D", h, "future")
+        yh = mmf.alloc_packed(ne, t)                      # pinned, pitched
+        oh = mmf.pinned_empty((ne, h))
+        yh[...] = y[:ne].cpu().numpy()
+        Ke = min(K, 10)
+        for _ in range(2):
+            eng2.fit_forecast(yh, ps, npred, out=oh)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            eng2.fit_forecast(yh, ps, npred, out=oh)      # returns when the forecasts are in host memory
+        te = time.perf_counter() - t0
+        tte = torch.tensor([te], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tte, op=dist.ReduceOp.MAX)
+        te = float(tte[0])
+        chk = float(np.abs(oh[:4096] - table[rank * n: rank * n + 4096].cpu().numpy()).max())
+        e2e = {"value": world * ne * Ke / te, "unit": UNIT, "h2d_bytes_per_step": ne * t * 4,
+               "d2h_bytes_per_step": ne * h * 4, "series_per_step_per_gpu": ne, "steps": Ke,
+               "ms_per_step": 1e3 * te / Ke, "max_abs_diff_vs_device_path": chk,
+               "api": "mmf_fit_forecast_f32 with pinned host y/out (ForecastEngine.fit_forecast on NumPy arrays)"}
+        eng2.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_port_baseline(y[:100000].cpu().numpy(), start, t, h)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{n} (store,item) series x {t} days per GPU, {h}-day horizon, future mode "
+                                       f"(BASELINE configs[3] shape; weak scaling)",
+                           "series_per_gpu": n, "t": t, "horizon": h, "nan_frac": args.nan_frac,
+                           "kernel": kernel_used, "l2": f"inputs {n * t * 4 / 1e9:.2f} GB per step per GPU > 126 MB L2",
+                           "parallelism": f"series-sharded x{world}" + (" + one NCCL all_gather of the forecast table" if world > 1 else "")},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": launches_per_call * K, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -92,7 +92,7 @@ def pack_groups(pdf: pd.DataFrame, keys=DEFAULT_KEYS, date_col="Date", value_col
     if len(pdf) == 0:
         return []
     days = D.as_days(pdf[date_col].to_numpy()).astype(np.int64)
-    gid, uniq = pd.factorize(pd.MultiIndex.from_frame(pdf[keys]), sort=True)
+    gid, uniq = pd.MultiIndex.from_frame(pdf[keys]).factorize(sort=True)
     n_groups = len(uniq)
     vals = pdf[value_col].to_numpy(dtype=np.float32, na_value=np.nan)
     gmin = np.full(n_groups, np.iinfo(np.int64).max)
@@ -105,9 +105,9 @@ def pack_groups(pdf: pd.DataFrame, keys=DEFAULT_KEYS, date_col="Date", value_col
     off = days - gmin[gid]
     on_grid = off % step == 0                       # off-grid rows vanish under asfreq
     pos = off // step
-    key_frame = uniq.to_frame(index=False)
+    key_frame = pd.DataFrame(list(uniq), columns=keys)
     buckets = []
-    bucket_id, bucket_keys = pd.factorize(pd.MultiIndex.from_arrays([gmin, t_len]), sort=True)
+    bucket_id, bucket_keys = pd.MultiIndex.from_arrays([gmin, t_len]).factorize(sort=True)
     for b, (start_day, tl) in enumerate(bucket_keys):
         members = np.flatnonzero(bucket_id == b)
         local = np.full(n_groups, -1, dtype=np.int64)

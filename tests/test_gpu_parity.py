@@ -1,0 +1,276 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI (ctypes -> libmmf.so), against the float64
+oracle on identical seeded inputs, the frozen golden vectors, and size-independent properties at
+BASELINE.json's sizes.  Tolerance (stated): |yhat_gpu - yhat_ref| <= 1e-4*max|y| + 1e-3."""
+import datetime as dt
+
+import numpy as np
+import pytest
+
+import mmf
+from conftest import tolerance
+from oracle import mmf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engines():
+    e = {k: mmf.ForecastEngine(kernel=k) for k in ("auto", "warp", "tc")}
+    yield e
+    for x in e.values():
+        x.close()
+
+
+def _oracle(y, start, freq, horizon, mode):
+    T = y.shape[1]
+    if mode == "holdout":
+        grid = O.calendar_grid(start, T, freq)
+        return O.fit_forecast_packed(y, O.design_matrix(grid, T - horizon), T - horizon, 0, T)
+    grid = O.calendar_grid(start, T + horizon, freq)
+    return O.fit_forecast_packed(y, O.design_matrix(grid, T), T, T, horizon)
+
+
+def _run(eng, y, start, freq, horizon, mode, **kw):
+    import torch
+    yd = torch.from_numpy(np.ascontiguousarray(y)).cuda()
+    res = mmf.forecast_packed(yd, start, freq, horizon, mode, engine=eng, want_status=True, **kw)
+    torch.cuda.synchronize()
+    eng.synchronize()
+    return res["pred"].cpu().numpy(), res["status"].cpu().numpy(), res
+
+
+# ---- frozen golden vectors -------------------------------------------------------------------------
+def test_golden_reference_weekly_holdout(engines, oracle_golden):
+    g = oracle_golden
+    y = g["ref_weekly_y"]
+    start = g["ref_weekly_start"][0].astype("datetime64[D]")
+    for k in ("auto", "warp"):
+        pred, status, _ = _run(engines[k], y, start, "W-MON", 40, "holdout")
+        assert np.abs(pred - g["ref_weekly_fitted"]).max() <= tolerance(y)
+        assert np.array_equal(status, g["ref_weekly_status"])
+
+
+def test_golden_daily365_future_with_gaps(engines, oracle_golden):
+    g = oracle_golden
+    y = g["daily365_y"]
+    start = g["daily365_start"][0].astype("datetime64[D]")
+    for k in ("auto", "warp", "tc"):
+        pred, status, _ = _run(engines[k], y, start, "D", 28, "future")
+        assert np.abs(pred - g["daily365_pred"]).max() <= tolerance(y), k
+        assert np.array_equal(status, g["daily365_status"]), k
+
+
+def test_golden_daily1095(engines, oracle_golden):
+    g = oracle_golden
+    y = g["daily1095_y"]
+    start = g["daily1095_start"][0].astype("datetime64[D]")
+    for k in ("auto", "warp", "tc"):
+        pred, _, _ = _run(engines[k], y, start, "D", 28, "future")
+        assert np.abs(pred - g["daily1095_future"]).max() <= tolerance(y), k
+    pred, _, _ = _run(engines["auto"], y, start, "D", 28, "holdout")
+    assert np.abs(pred - g["daily1095_holdout"]).max() <= tolerance(y)
+
+
+# ---- seeded parity, every kernel, BASELINE config 2 shape (10k x 1095 is covered below at reduced N) --
+@pytest.mark.parametrize("kernel", ["warp", "tc", "auto"])
+@pytest.mark.parametrize("n,t", [(1, 1095), (127, 1095), (128, 1095), (129, 1095), (1000, 1095), (300, 365), (64, 33),
+                                 (40, 32), (9, 5)])
+def test_parity_full_series(engines, kernel, n, t):
+    y, start = mmf.synth.daily_store_item_demand(n, t, seed=100 + n + t)
+    want, wst = _oracle(y, start, "D", 28, "future")
+    pred, status, _ = _run(engines[kernel], y, start, "D", 28, "future")
+    assert np.abs(pred - want).max() <= tolerance(y)
+    assert np.array_equal(status, wst)
+
+
+def test_parity_config2_10k_by_1095(engines):
+    """BASELINE.json configs[1]: 10k groups x 1,095 days fp32, single B200, parity on ALL series."""
+    y, start = mmf.synth.daily_store_item_demand(10_000, 1095, seed=1234)
+    want, _ = _oracle(y, start, "D", 28, "future")
+    for k in ("tc", "warp"):
+        pred, status, res = _run(engines[k], y, start, "D", 28, "future", want_stats=True)
+        err = np.abs(pred - want)
+        assert err.max() <= tolerance(y), (k, err.max())
+        assert (status == 0).all()
+        assert res["stats"].kernel_used == k
+
+
+@pytest.mark.parametrize("kernel", ["warp", "auto", "tc"])
+def test_parity_masked_series(engines, kernel):
+    y, start = mmf.synth.daily_store_item_demand(300, 1095, seed=7, nan_frac=0.02)
+    y[5, :400] = np.nan          # long leading gap
+    y[6, 700:] = np.nan          # long trailing gap
+    y[7, ::2] = np.nan           # every other day
+    y[8, 100] = np.inf           # Inf == missing
+    want, wst, _, ratio = O.fit_forecast_packed(y, *_design(start, 1095, 28), return_gamma=True)
+    pred, status, res = _run(engines[kernel], y, start, "D", 28, "future", want_stats=True)
+    # ill-conditioned masks amplify fp32 rounding by ~1/min_pivot_ratio; scale the stated tolerance by it
+    tol = tolerance(y) / np.minimum(1.0, ratio / 0.25)
+    assert (np.abs(pred - want).max(axis=1) <= tol).all()
+    assert np.array_equal(status, wst)
+    if kernel != "warp":
+        assert res["stats"].n_pending == 300
+
+
+def _design(start, t, h):
+    grid = O.calendar_grid(start, t + h, "D")
+    return O.design_matrix(grid, t), t, t, h
+
+
+def test_empty_single_and_rank_deficient_rows(engines):
+    t, h = 200, 28
+    start = dt.date(2019, 1, 1)
+    y = np.full((6, t), np.nan, dtype=np.float32)
+    y[1, 17] = 7.5                                   # one observation
+    y[2] = 100 + 2 * np.arange(t)                    # a clean line
+    y[3] = y[2]; y[3, 5:60] = np.nan                 # line with a hole
+    y[4, 150:] = 50 + np.arange(50)                  # short tail only
+    y[5] = 42.0
+    want, wst = O.fit_forecast_packed(y, *_design(start, t, h))
+    for k in ("warp", "auto", "tc"):
+        pred, status, _ = _run(engines[k], y, start, "D", h, "future")
+        assert np.array_equal(status, wst), k
+        assert np.isnan(pred[0]).all()
+        assert np.abs(pred[1] - 7.5).max() < 1e-3
+        assert np.abs(pred[2] - (100 + 2 * np.arange(t, t + h))).max() < 0.05
+        assert np.abs(pred[3] - (100 + 2 * np.arange(t, t + h))).max() < 0.05
+        assert np.abs(pred[5] - 42.0).max() < 1e-3
+        ok = wst != 1
+        assert np.abs(pred[ok] - want[ok]).max() <= 0.05, k
+
+
+def test_beta_reproduces_fitted_values(engines):
+    y, start = mmf.synth.daily_store_item_demand(50, 400, seed=3)
+    eng = engines["warp"]
+    days, ps, npred = eng.plan_calendar(start, 400, "D", 28, "holdout")
+    import torch
+    res = eng.fit_forecast(torch.from_numpy(y).cuda(), ps, npred, want_beta=True)
+    eng.synchronize()
+    X = mmf.design.design_matrix(mmf.design.calendar_grid(start, 400, "D"), 372)
+    fitted = res["beta"].cpu().numpy().astype(np.float64) @ X.T
+    assert np.abs(fitted - res["pred"].cpu().numpy()).max() <= 5 * tolerance(y)
+    res_tc = mmf.forecast_packed(torch.from_numpy(y).cuda(), start, "D", 28, "future", engine=engines["tc"], want_beta=True)
+    res_w = mmf.forecast_packed(torch.from_numpy(y).cuda(), start, "D", 28, "future", engine=engines["warp"], want_beta=True)
+    engines["tc"].synchronize(); engines["warp"].synchronize()
+    assert np.abs(res_tc["beta"].cpu().numpy() - res_w["beta"].cpu().numpy()).max() <= 1e-2 * np.abs(res_w["beta"].cpu().numpy()).max()
+
+
+# ---- host-buffer (C ABI with HOST pointers) path: pipelined chunks == device path --------------------
+def test_host_buffer_path_matches_device_path():
+    y, start = mmf.synth.daily_store_item_demand(5000, 365, seed=9, nan_frac=0.001)
+    eng = mmf.ForecastEngine(chunk_series=700)        # forces 8 chunks through 3 staging buffers
+    _, ps, npred = eng.plan_calendar(start, 365, "D", 28, "future")
+    yp = mmf.alloc_packed(5000, 365)                  # pinned, pitched
+    yp[...] = y
+    res = eng.fit_forecast(yp, ps, npred, want_status=True, want_beta=True, want_stats=True)
+    assert isinstance(res["pred"], np.ndarray) and res["stats"].h2d_bytes == 5000 * 365 * 4
+    import torch
+    dev = eng.fit_forecast(torch.from_numpy(y).cuda(), ps, npred, want_status=True, want_beta=True)
+    eng.synchronize()
+    assert np.array_equal(res["pred"], dev["pred"].cpu().numpy(), equal_nan=True)
+    assert np.array_equal(res["status"], dev["status"].cpu().numpy())
+    assert np.array_equal(res["beta"], dev["beta"].cpu().numpy(), equal_nan=True)
+    # pageable, unpadded host array (T=365 is not a multiple of 4): the library re-pitches while staging
+    res2 = eng.fit_forecast(np.ascontiguousarray(y), ps, npred)
+    assert np.array_equal(res2, res["pred"], equal_nan=True)
+    eng.close()
+
+
+# ---- size-independent properties at BASELINE sizes -----------------------------------------------------
+@pytest.mark.parametrize("kernel", ["tc", "warp"])
+def test_properties_at_100k_by_1095(engines, kernel):
+    """configs[2] shape: linearity, shift equivariance, row-permutation equivariance, exact lines."""
+    import torch
+    n, t, h = 100_000, 1095, 28
+    yd, start = mmf.synth.daily_store_item_demand_torch(n, t, seed=42)
+    eng = engines[kernel]
+    _, ps, npred = eng.plan_calendar(start, t, "D", h, "future")
+    f = lambda z: eng.fit_forecast(z, ps, npred)
+    base = f(yd)
+    scale = float(yd.abs().max())
+    tol = 1e-4 * scale + 1e-3
+    # shift equivariance (intercept in the span): f(y + c) = f(y) + c
+    assert float((f(yd + 1000.0) - (base + 1000.0)).abs().max()) <= 2 * tol
+    # linearity: f(2y - 3z) = 2 f(y) - 3 f(z) with z a row-rolled copy
+    z = torch.roll(yd, 1, 0).contiguous()
+    zz = torch.empty_like(yd); zz.copy_(z)
+    lin = f(2.0 * yd - 3.0 * zz)
+    assert float((lin - (2.0 * base - 3.0 * torch.roll(base, 1, 0))).abs().max()) <= 8 * tol
+    # exact answer: rows that are pure lines forecast the line
+    tt = torch.arange(t + h, device="cuda", dtype=torch.float32)
+    lines = torch.empty_like(yd[:4096])
+    a = torch.linspace(100, 20000, 4096, device="cuda")[:, None]
+    b = torch.linspace(-5, 5, 4096, device="cuda")[:, None]
+    lines.copy_(a + b * tt[None, :t])
+    out = f(lines)
+    assert float((out - (a + b * tt[None, t:])).abs().max()) <= tol
+    eng.synchronize()
+
+
+def test_tc_and_warp_agree_on_1m_rows(engines):
+    """configs[3] size on one GPU: the two independent CUDA implementations agree row by row."""
+    import torch
+    n, t, h = 1_000_000, 1095, 28
+    yd, start = mmf.synth.daily_store_item_demand_torch(n, t, seed=43)
+    outs = {}
+    for k in ("tc", "warp"):
+        eng = engines[k]
+        _, ps, npred = eng.plan_calendar(start, t, "D", h, "future")
+        outs[k] = eng.fit_forecast(yd, ps, npred)
+        eng.synchronize()
+    tol = 1e-4 * float(yd.abs().max()) + 1e-3
+    assert float((outs["tc"] - outs["warp"]).abs().max()) <= tol
+    # and a sampled slice against the oracle
+    idx = torch.randint(0, n, (512,), device="cuda")
+    ys = yd[idx].cpu().numpy()
+    want, _ = _oracle(ys, start, "D", h, "future")
+    assert np.abs(outs["tc"][idx].cpu().numpy() - want).max() <= tol
+
+
+# ---- the DataFrame / Arrow boundary ---------------------------------------------------------------------
+def test_forecast_groups_matches_reference_shaped_udf():
+    df = mmf.synth.reference_weekly_demand(n_skus=3)
+    df = df[~((df["SKU"] == df["SKU"].iloc[0]) & (df["Date"] == dt.date(2019, 5, 6)))]   # one gap
+    got = mmf.forecast_groups(df.sample(frac=1.0, random_state=0))                       # defaults = 02:341,526
+    want = O.fanout_apply(df, O.build_tune_and_score_model, ("Product", "SKU"))
+    assert list(got.columns) == ["Product", "SKU", "Date", "Demand", "Demand_Fitted"]
+    assert len(got) == len(want) == 15 * 157
+    assert (got["Product"].to_numpy() == want["Product"].to_numpy()).all()
+    assert (got["SKU"].to_numpy() == want["SKU"].to_numpy()).all()
+    assert (got["Date"].dt.date.to_numpy() == want["Date"].to_numpy()).all()
+    assert np.array_equal(got["Demand"].to_numpy(), want["Demand"].to_numpy(), equal_nan=True)
+    assert got["Demand_Fitted"].dtype == np.float32
+    tol = tolerance(df["Demand"].to_numpy())
+    assert np.abs(got["Demand_Fitted"].to_numpy() - want["Demand_Fitted"].to_numpy()).max() <= tol
+    # single group == literal applyInPandas drop-in (02:527)
+    one = df[df["SKU"] == df["SKU"].iloc[-1]]
+    g1 = mmf.forecast_groups(one)
+    w1 = O.build_tune_and_score_model(one)
+    assert np.abs(g1["Demand_Fitted"].to_numpy() - w1["Demand_Fitted"].to_numpy()).max() <= tol
+
+
+def test_forecast_groups_config1_daily_100x365_and_arrow():
+    """BASELINE.json configs[0]: 100 (store,item) groups x 365 days through the DataFrame boundary."""
+    import pandas as pd
+    import pyarrow as pa
+    y, start = mmf.synth.daily_store_item_demand(100, 365, seed=5)
+    days = mmf.design.calendar_grid(start, 365, "D")
+    df = pd.DataFrame({"store": np.repeat([f"s{i // 10}" for i in range(100)], 365),
+                       "item": np.repeat([f"i{i:03d}" for i in range(100)], 365),
+                       "date": np.tile(days, 100), "sales": y.reshape(-1)})
+    kw = dict(keys=("store", "item"), date_col="date", value_col="sales", freq="D", horizon=28, mode="future")
+    got = mmf.forecast_groups(df, **kw)
+    assert len(got) == 100 * 28 and got["sales"].isna().all()
+    want, _ = _oracle(y, start, "D", 28, "future")
+    assert np.abs(got["sales_Fitted"].to_numpy().reshape(100, 28) - want).max() <= tolerance(y)
+    tbl = mmf.forecast_table(pa.Table.from_pandas(df), **kw)
+    assert tbl.schema.names == ["store", "item", "date", "sales", "sales_Fitted"]
+    assert tbl.schema.field("date").type == pa.date32() and tbl.schema.field("sales_Fitted").type == pa.float32()
+    assert tbl.num_rows == 2800
+
+
+def test_exog_only_design_on_gpu(engines):
+    df = mmf.synth.reference_weekly_demand(n_skus=1)
+    got = mmf.forecast_groups(df, design="exog_only")
+    want = O.fanout_apply(df, lambda g: O.build_tune_and_score_model(g, design="exog_only"), ("Product", "SKU"))
+    assert np.abs(got["Demand_Fitted"].to_numpy() - want["Demand_Fitted"].to_numpy()).max() <= tolerance(df["Demand"].to_numpy())
