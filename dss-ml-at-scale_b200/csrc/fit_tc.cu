@@ -102,47 +102,44 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
 
   if (warp == 4) {
     // =========================== TMA producer ===========================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int ch = 0; ch < n_chunks; ++ch) {
-          mbar_wait(bar_empty(stage), phase ^ 1u);
-          mbar_expect_tx(bar_full(stage), Y_STAGE_BYTES + AT_STAGE_BYTES);
-          tma_load_2d(s_y + stage * Y_STAGE_BYTES, tl.tmap_y, bar_full(stage), ch * KC, tile * TILE_M,
-                      L2_EVICT_FIRST);
-          tma_load_2d(s_at + stage * AT_STAGE_BYTES, tl.tmap_at, bar_full(stage), ch * KC, 0, L2_EVICT_LAST);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-        }
+    // whole warp converged, one elected lane issues (keeps the tensor-map / barrier operands uniform)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        mbar_wait(bar_empty(stage), phase ^ 1u);
+        tma_load_2d_x2_elect(bar_full(stage), Y_STAGE_BYTES + AT_STAGE_BYTES,
+                             s_y + stage * Y_STAGE_BYTES, tl.tmap_y, ch * KC, tile * TILE_M, L2_EVICT_FIRST,
+                             s_at + stage * AT_STAGE_BYTES, tl.tmap_at, ch * KC, 0, L2_EVICT_LAST);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 5) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      constexpr uint32_t IDESC_N32 = umma_idesc_tf32(TILE_M, 2 * P);
-      constexpr uint32_t IDESC_N16 = umma_idesc_tf32(TILE_M, P);
-      int stage = 0, aslot = 0;
-      uint32_t phase = 0, aphase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int ch = 0; ch < n_chunks; ++ch) {
-          mbar_wait(bar_full(stage), phase);          // design chunk landed (same barrier as the y box)
-          mbar_wait(bar_afull(aslot), aphase);        // A operand written to TMEM by the transform warps
-          tc_fence_after();
-          const uint32_t b_addr = s_at + stage * AT_STAGE_BYTES;
-          const uint32_t a_hi = tmem_base + ASLOT_COL0 + aslot * 64;
-          const uint32_t a_lo = a_hi + 32;
+    // whole warp converged; tcgen05.mma / commit are predicated on elect.sync inside the wrappers
+    constexpr uint32_t IDESC_N32 = umma_idesc_tf32(TILE_M, 2 * P);
+    constexpr uint32_t IDESC_N16 = umma_idesc_tf32(TILE_M, P);
+    int stage = 0, aslot = 0;
+    uint32_t phase = 0, aphase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        mbar_wait(bar_full(stage), phase);          // design chunk landed (same barrier as the y box)
+        mbar_wait(bar_afull(aslot), aphase);        // A operand written to TMEM by the transform warps
+        tc_fence_after();
+        const uint64_t bdesc0 = umma_desc_k_sw128(s_at + stage * AT_STAGE_BYTES);
+        const uint32_t a_hi = tmem_base + ASLOT_COL0 + aslot * 64;
+        const uint32_t a_lo = a_hi + 32;
 #pragma unroll
-          for (int k = 0; k < KC / 8; ++k) {
-            const uint64_t bdesc = umma_desc_k_sw128(b_addr + k * 32);
-            umma_tf32_ts(tmem_base + ACC_COL, a_hi + k * 8, bdesc, IDESC_N32, (ch | k) != 0 ? 1u : 0u);
-            umma_tf32_ts(tmem_base + ACC_COL, a_lo + k * 8, bdesc, IDESC_N16, 1u);
-          }
-          umma_commit(bar_aempty(aslot));
-          umma_commit(bar_empty(stage));
-          if (ch == n_chunks - 1) umma_commit(bar_acc);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-          if (++aslot == ASLOTS) { aslot = 0; aphase ^= 1u; }
+        for (int k = 0; k < KC / 8; ++k) {
+          const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(k * 2);       // +32 B (16-B units)
+          umma_tf32_ts_elect(tmem_base + ACC_COL, a_hi + k * 8, bdesc, IDESC_N32, (ch | k) != 0 ? 1u : 0u);
+          umma_tf32_ts_elect(tmem_base + ACC_COL, a_lo + k * 8, bdesc, IDESC_N16, 1u);
         }
+        umma_commit_elect(bar_aempty(aslot));
+        umma_commit_elect(bar_empty(stage));
+        if (ch == n_chunks - 1) umma_commit_elect(bar_acc);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        if (++aslot == ASLOTS) { aslot = 0; aphase ^= 1u; }
       }
     }
   } else {

@@ -117,6 +117,7 @@ fit_warp_kernel(const DesignView d, const FitArgs a, const int smem_rows) {
 #pragma unroll
     for (int k = 0; k < DPL; ++k) dacc[k] = 0.f;
     unsigned anymiss = 0u;
+    int nmiss = 0;
 
     for (int t0 = 0; t0 < t_fit; t0 += 32 * U) {
       float v[U];
@@ -144,6 +145,7 @@ fit_warp_kernel(const DesignView d, const FitArgs a, const int smem_rows) {
           acc[14] = fmaf(a3.z, r, acc[14]); acc[15] = fmaf(a3.w, r, acc[15]);
           unsigned mm = __ballot_sync(0xffffffffu, inr && !fin);
           anymiss |= mm;
+          nmiss += __popc(mm);
           while (mm) {                             // rare: Gram downdate for each missing t
             const int tt = tb + __ffs(mm) - 1;
             mm &= mm - 1;
@@ -165,6 +167,25 @@ fit_warp_kernel(const DesignView d, const FitArgs a, const int smem_rows) {
       for (int p = 0; p < P; ++p) g[p] = ((d.kept_mask >> p) & 1u) ? acc[p] : 0.f;
     } else {
       // ---- per-series normal equations in shared memory
+      // Mostly-missing rows: G_i = I - D would cancel catastrophically in fp32, so re-accumulate the
+      // Gram directly over the (few) observed rows instead of downdating over the (many) missing ones.
+      const bool direct = 2 * nmiss > t_fit;
+      if (direct) {
+#pragma unroll
+        for (int k = 0; k < DPL; ++k) dacc[k] = 0.f;
+        for (int t0 = 0; t0 < t_fit; t0 += 32) {
+          const int t = t0 + lane;
+          const float v = (t < t_fit) ? __ldg(yr + t) : __int_as_float(0x7fc00000);
+          unsigned mm = __ballot_sync(0xffffffffu, is_finite_bits(v));
+          while (mm) {
+            const int tt = t0 + __ffs(mm) - 1;
+            mm &= mm - 1;
+#pragma unroll
+            for (int k = 0; k < DPL; ++k)
+              dacc[k] = fmaf(A.elem(tt, pi[k]), A.elem(tt, pj[k]), dacc[k]);
+          }
+        }
+      }
       __syncwarp();
 #pragma unroll
       for (int k = 0; k < DPL; ++k) {
@@ -172,7 +193,7 @@ fit_warp_kernel(const DesignView d, const FitArgs a, const int smem_rows) {
         if (e < NPAIR) {
           const int i = pi[k], j = pj[k];
           const float full = (i == j && ((d.kept_mask >> i) & 1u)) ? 1.f : 0.f;
-          const float gij = full - dacc[k];
+          const float gij = direct ? dacc[k] : full - dacc[k];
           scr.G[i][j] = gij;
           scr.G[j][i] = gij;
           if (i == j) scr.diag0[i] = gij;

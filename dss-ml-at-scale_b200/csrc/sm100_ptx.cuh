@@ -64,6 +64,24 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tmap,
       : "memory");
 }
 
+// warp-converged: all lanes call with warp-uniform operands, one elected lane arms the barrier and issues
+__device__ __forceinline__ void tma_load_2d_x2_elect(uint32_t bar, uint32_t tx_bytes,
+                                                     uint32_t dst0, const void* tmap0, int32_t c00, int32_t c01, uint64_t hint0,
+                                                     uint32_t dst1, const void* tmap1, int32_t c10, int32_t c11, uint64_t hint1) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
+      "@pe cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%2], [%3, {%4, %5}], [%0], %6;\n\t"
+      "@pe cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%7], [%8, {%9, %10}], [%0], %11;\n\t}"
+      ::"r"(bar), "r"(tx_bytes),
+        "r"(dst0), "l"(reinterpret_cast<uint64_t>(tmap0)), "r"(c00), "r"(c01), "l"(hint0),
+        "r"(dst1), "l"(reinterpret_cast<uint64_t>(tmap1)), "r"(c10), "r"(c11), "l"(hint1)
+      : "memory");
+}
+
 // ---- TMEM ------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {   // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
@@ -144,6 +162,37 @@ __device__ __forceinline__ void umma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, u
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Warp-converged variants: every lane executes the call with warp-uniform operands, one elected lane
+// issues.  Keeps descriptors in uniform registers (a single-lane divergent issue path makes ptxas emit
+// a VOTEU/ELECT/R2UR waterfall around every UTCHMMA).
+__device__ __forceinline__ void umma_tf32_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                                   uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred pe, pa;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, pa;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ss_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                   uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred pe, pa;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, pa;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(bar)
       : "memory");
 }
 // all previously issued tcgen05 async ops of this thread arrive (once) on the mbarrier when done

@@ -150,6 +150,78 @@ __global__ void __launch_bounds__(160, 1) probe_kernel(const __grid_constant__ M
   }
 }
 
+
+// ---- timing probe: cycles per tcgen05.mma (M=128, K=8 tf32) for dependent vs independent accumulators,
+// issued the production way: warp-converged, one elected lane, descriptors in uniform registers.
+template <int NCOLS, int NACC, bool SS>
+__global__ void __launch_bounds__(160, 1) timing_kernel(long long* __restrict__ cycles, int niter) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  const uint32_t s_a = smem_u32(smem);
+  const uint32_t s_b = s_a + 16384;
+  const uint32_t bar = s_b + 8192;
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + 16384 + 8192 + 64);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < (16384 + 8192) / 4; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = 1.0f;
+  if (warp == 4) {
+    if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    __syncwarp();
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr)), 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  if (warp < 4) {
+    uint32_t z[32];
+    for (int i = 0; i < 32; ++i) z[i] = 0u;
+    const uint32_t la = static_cast<uint32_t>(warp * 32) << 16;
+    for (int c = 0; c < 512; c += 32) tmem_st_32x32b_x32(tmem + la + c, z);
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 4) {
+    constexpr uint32_t idesc = umma_idesc_tf32(128, NCOLS);
+    constexpr int STRIDE = NCOLS > 32 ? 64 : 32;
+    const uint64_t bd0 = umma_desc_k_sw128(s_b);
+    const uint64_t ad0 = umma_desc_k_sw128(s_a);
+    const long long t0 = clock64();
+    for (int it = 0; it < niter; it += 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t d = tmem + (j % NACC) * STRIDE;
+        const uint64_t bd = bd0 + static_cast<uint64_t>((j & 3) * 2);      // +32 B in 16-B units
+        if (SS) umma_tf32_ss_elect(d, ad0 + static_cast<uint64_t>((j & 3) * 2), bd, idesc, 1u);
+        else umma_tf32_ts_elect(d, tmem + 256 + (j & 3) * 8, bd, idesc, 1u);
+      }
+    }
+    const long long t1 = clock64();
+    umma_commit_elect(bar);
+    mbar_wait(bar, 0);
+    const long long t2 = clock64();
+    if (lane == 0) { cycles[0] = t1 - t0; cycles[1] = t2 - t0; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+template <int NCOLS, int NACC, bool SS>
+int run_timing(long long* dcy, int niter) {
+  long long h[2];
+  cudaFuncSetAttribute(timing_kernel<NCOLS, NACC, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 40960);
+  timing_kernel<NCOLS, NACC, SS><<<1, 160, 40960>>>(dcy, niter);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("timing kernel failed: %s\n", cudaGetErrorString(e)); return 3; }
+  cudaMemcpy(h, dcy, 16, cudaMemcpyDeviceToHost);
+  printf("  %s N=%3d accumulators=%d : %6.1f | %6.1f\n", SS ? "SS" : "TS", NCOLS, NACC, (double)h[0] / niter, (double)h[1] / niter);
+  return 0;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -223,6 +295,19 @@ int main() {
       }
     printf("mode %d: max|err| = %.3e (max|ref| = %.3e)  %s\n", mode, maxerr, maxref, bad ? "FAIL" : "ok");
     bad_total += bad;
+  }
+  {
+    long long* dcy;
+    CK(cudaMalloc(&dcy, 16));
+    const int niter = 4096;
+    printf("tcgen05.mma timing, M=128 K=8 tf32, %d MMAs, elected lane of a converged warp (issue cyc/MMA | issue+retire cyc/MMA)\n", niter);
+    run_timing<16, 1, false>(dcy, niter); run_timing<16, 2, false>(dcy, niter); run_timing<16, 4, false>(dcy, niter); run_timing<16, 8, false>(dcy, niter);
+    run_timing<32, 1, false>(dcy, niter); run_timing<32, 2, false>(dcy, niter); run_timing<32, 4, false>(dcy, niter); run_timing<32, 8, false>(dcy, niter);
+    run_timing<64, 1, false>(dcy, niter); run_timing<64, 4, false>(dcy, niter);
+    run_timing<128, 1, false>(dcy, niter); run_timing<256, 1, false>(dcy, niter);
+    run_timing<16, 1, true>(dcy, niter); run_timing<16, 8, true>(dcy, niter);
+    run_timing<32, 1, true>(dcy, niter); run_timing<32, 8, true>(dcy, niter);
+    run_timing<64, 1, true>(dcy, niter); run_timing<256, 1, true>(dcy, niter);
   }
   printf(bad_total ? "PROBE FAIL\n" : "PROBE OK\n");
   return bad_total ? 1 : 0;

@@ -59,6 +59,19 @@ def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
     return arr
 
 
+def device_packed(y, device="cuda"):
+    """Copy packed series (NumPy [n,t] or torch) into a CUDA tensor whose row pitch is a multiple of
+    4 floats -- the layout the TMA/tcgen05 fast path needs.  Returns the [n, t] view."""
+    import torch
+
+    src = torch.from_numpy(np.ascontiguousarray(y)) if isinstance(y, np.ndarray) else y
+    n, t = src.shape
+    full = torch.empty((n, (t + 3) & ~3), dtype=torch.float32, device=device)
+    view = full[:, :t]
+    view.copy_(src)
+    return view
+
+
 def alloc_packed(n: int, t: int, pinned: bool = True):
     """Host buffer for ``n`` packed series of length ``t`` with a TMA-friendly row pitch
     (multiple of 4 floats).  Returns the [n, t] view; ``view.base`` keeps the padded rows."""
@@ -163,6 +176,9 @@ class ForecastEngine:
             import torch
             if y.dtype != torch.float32:
                 raise TypeError("y must be float32")
+            if on_dev:
+                # stream-ordered with the caller's torch work: enqueue on torch's current stream
+                self.set_stream(torch.cuda.current_stream(y.device).cuda_stream)
         elif y.dtype != np.float32:
             raise TypeError("y must be float32")
 

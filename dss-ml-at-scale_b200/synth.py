@@ -153,7 +153,7 @@ def daily_store_item_demand_torch(n: int, t_len: int, seed: int = 1234, nan_frac
     pre_t = torch.tensor(pre, device=device)
     sq = torch.sqrt(torch.arange(t_len, **f32))
     wd_t = torch.tensor(wd, device=device, dtype=torch.long)
-    block = 131072
+    block = 1 << 20                       # one pass for the bench size: ~2.2k launches for the AR recursion
     for i0 in range(0, n, block):
         m = min(block, n - i0)
         level = torch.clamp(torch.abs(torch.randn(m, generator=g, **f32) * 5000 + 10000), min=4000)
