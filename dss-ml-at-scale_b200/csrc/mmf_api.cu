@@ -464,8 +464,11 @@ int mmf_fit_forecast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, 
       if (y_dev) { yk = y + off * ld_y; ldk = ld_y; }
       else {
         if (it >= NBUF) CU_TRY(cudaStreamWaitEvent(ctx->s_h2d, s.ev_comp, 0));     // staging buffer free again
-        CU_TRY(cudaMemcpy2DAsync(s.d_y, (size_t)pitch * 4, y + off * ld_y, (size_t)ld_y * 4, (size_t)pl.t_fit * 4,
-                                 (size_t)m, cudaMemcpyHostToDevice, ctx->s_h2d));
+        if (ld_y == pitch)        // already pitched on the host: one contiguous copy (pad columns ride along)
+          CU_TRY(cudaMemcpyAsync(s.d_y, y + off * ld_y, (size_t)m * pitch * 4, cudaMemcpyHostToDevice, ctx->s_h2d));
+        else
+          CU_TRY(cudaMemcpy2DAsync(s.d_y, (size_t)pitch * 4, y + off * ld_y, (size_t)ld_y * 4, (size_t)pl.t_fit * 4,
+                                   (size_t)m, cudaMemcpyHostToDevice, ctx->s_h2d));
         CU_TRY(cudaEventRecord(s.ev_h2d, ctx->s_h2d));
         CU_TRY(cudaStreamWaitEvent(ctx->stream, s.ev_h2d, 0));
         yk = s.d_y; ldk = pitch;
@@ -482,8 +485,11 @@ int mmf_fit_forecast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, 
       bool any_d2h = false;
       if (!o_dev) {
         CU_TRY(cudaStreamWaitEvent(ctx->s_d2h, s.ev_comp, 0));
-        CU_TRY(cudaMemcpy2DAsync(out_pred + off * ld_out, (size_t)ld_out * 4, s.d_out, (size_t)opitch * 4,
-                                 (size_t)n_pred * 4, (size_t)m, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        if (ld_out == opitch && n_pred == opitch)
+          CU_TRY(cudaMemcpyAsync(out_pred + off * ld_out, s.d_out, (size_t)m * opitch * 4, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        else
+          CU_TRY(cudaMemcpy2DAsync(out_pred + off * ld_out, (size_t)ld_out * 4, s.d_out, (size_t)opitch * 4,
+                                   (size_t)n_pred * 4, (size_t)m, cudaMemcpyDeviceToHost, ctx->s_d2h));
         d2h += m * (int64_t)n_pred * 4; any_d2h = true;
       }
       if (out_beta && !b_dev) {
