@@ -221,13 +221,13 @@ def run_ours(args):
     for _ in range(W):
         step()
     torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:                       # start sampling BEFORE the barrier so every rank enters the timed loop together
+        sampler.start()
+        time.sleep(0.3)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K + 2)]
     torch.cuda.profiler.start()          # `ncu --profile-from-start off` captures exactly the timed region
     wall0 = time.time()
