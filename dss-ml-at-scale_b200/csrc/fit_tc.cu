@@ -27,13 +27,20 @@ using namespace sm100;
 
 constexpr int TILE_M = 128;            // series per tile == TMEM lanes
 constexpr int KC = 32;                 // time steps per stage == one 128-B swizzle row
-constexpr int STAGES = 8;
-constexpr int ASLOTS = 3;              // TMEM A-operand ring
+#ifndef MMF_TC_STAGES
+#define MMF_TC_STAGES 8
+#endif
+#ifndef MMF_TC_ASLOTS
+#define MMF_TC_ASLOTS 6
+#endif
+constexpr int STAGES = MMF_TC_STAGES;  // shared-memory ring (20 KB per stage)
+constexpr int ASLOTS = MMF_TC_ASLOTS;  // TMEM A-operand ring: covers the tcgen05.st -> mma -> commit round trip
 constexpr int MAX_PRED = 64;           // forecast rows the epilogue supports
 constexpr int Y_STAGE_BYTES = TILE_M * KC * 4;      // 16384
 constexpr int AT_STAGE_BYTES = 2 * P * KC * 4;      // 4096
 constexpr int THREADS = 192;
-constexpr uint32_t TMEM_COLS = 256;
+constexpr uint32_t TMEM_COLS = (32 + 64 * ASLOTS) <= 256 ? 256 : 512;
+static_assert(32 + 64 * ASLOTS <= 512, "TMEM holds 512 columns");
 constexpr uint32_t ACC_COL = 0;                     // 32 accumulator columns
 constexpr uint32_t ASLOT_COL0 = 32;                 // slot j: hi at 32+64j, lo at 32+64j+32
 

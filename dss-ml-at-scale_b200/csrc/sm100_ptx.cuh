@@ -38,11 +38,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a protocol bug traps (-> a CUDA error through the C ABI) instead of hanging the GPU.
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a protocol bug traps after ~2 s (-> a CUDA error through the C ABI) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins == (1u << 28)) __trap();
+    if ((++spins & 1023u) == 0u && global_timer_ns() - t0 > 2000000000ull) __trap();
   }
 }
 
@@ -79,6 +86,18 @@ __device__ __forceinline__ void tma_load_2d_x2_elect(uint32_t bar, uint32_t tx_b
       ::"r"(bar), "r"(tx_bytes),
         "r"(dst0), "l"(reinterpret_cast<uint64_t>(tmap0)), "r"(c00), "r"(c01), "l"(hint0),
         "r"(dst1), "l"(reinterpret_cast<uint64_t>(tmap1)), "r"(c10), "r"(c11), "l"(hint1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d_elect(uint32_t bar, uint32_t tx_bytes, uint32_t dst, const void* tmap,
+                                                  int32_t c0, int32_t c1, uint64_t hint) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
+      "@pe cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%2], [%3, {%4, %5}], [%0], %6;\n\t}"
+      ::"r"(bar), "r"(tx_bytes), "r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "l"(hint)
       : "memory");
 }
 
