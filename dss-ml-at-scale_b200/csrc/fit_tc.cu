@@ -10,12 +10,14 @@
 // Rows that contain a non-finite value poison only their own accumulator row (NaN/Inf); the epilogue
 // detects that, marks the row MMF_STATUS_PENDING and the masked warp kernel finishes them.
 //
-// CTA = 6 warps, 1 CTA per SM, persistent over 128-series tiles:
-//   warps 0-3  transform + epilogue: thread r owns series row r of the tile == TMEM lane r.
-//              LDS.128 its 128-B row of the TMA-swizzled stage, centre, split hi/lo, tcgen05.st the
-//              two 32-column A operands; at tile end tcgen05.ld the accumulators and write forecasts.
-//   warp 4     TMA producer: y box {32 t x 128 series} + design box {32 t x 32 (hi|lo columns)} per stage.
-//   warp 5     MMA issuer (one thread) + TMEM allocation.
+// CTA = 14 warps, 1 CTA per SM, persistent over 128-series tiles, every stage decoupled by mbarriers:
+//   warp 12    TMA producer: y box {32 t x 128 series} + design box {32 t x 32 (hi|lo columns)} per stage.
+//   warps 0-3 / 4-7   two transform groups taking alternate 32-step chunks.  Thread r owns series row r of
+//              the tile == TMEM lane r: LDS.128 its 128-B row of the TMA-swizzled stage, centre, split hi/lo,
+//              tcgen05.st the two 32-column A operands into the group's TMEM slot ring.
+//   warp 13    MMA issuer (warp-converged, elect.sync-predicated tcgen05.mma / commit) + TMEM allocation.
+//   warps 8-11 epilogue: tcgen05.ld the (double-buffered) accumulators of a finished tile, release them at
+//              once, then forecast + store while the next tile is already streaming.
 // Algorithmic HBM bytes per series: 4*t_fit read + 4*n_pred written.
 #include "mmf_internal.cuh"
 #include "sm100_ptx.cuh"
@@ -25,24 +27,27 @@ namespace {
 
 using namespace sm100;
 
-constexpr int TILE_M = 128;            // series per tile == TMEM lanes
-constexpr int KC = 32;                 // time steps per stage == one 128-B swizzle row
 #ifndef MMF_TC_STAGES
-#define MMF_TC_STAGES 8
+#define MMF_TC_STAGES 10
 #endif
 #ifndef MMF_TC_ASLOTS
-#define MMF_TC_ASLOTS 6
+#define MMF_TC_ASLOTS 2
 #endif
+constexpr int TILE_M = 128;            // series per tile == TMEM lanes
+constexpr int KC = 32;                 // time steps per stage == one 128-B swizzle row
 constexpr int STAGES = MMF_TC_STAGES;  // shared-memory ring (20 KB per stage)
-constexpr int ASLOTS = MMF_TC_ASLOTS;  // TMEM A-operand ring: covers the tcgen05.st -> mma -> commit round trip
+constexpr int NGROUPS = 2;             // transform groups (alternate chunks)
+constexpr int ASLOTS = MMF_TC_ASLOTS;  // TMEM A-operand slots per transform group
 constexpr int MAX_PRED = 64;           // forecast rows the epilogue supports
 constexpr int Y_STAGE_BYTES = TILE_M * KC * 4;      // 16384
 constexpr int AT_STAGE_BYTES = 2 * P * KC * 4;      // 4096
-constexpr int THREADS = 192;
-constexpr uint32_t TMEM_COLS = (32 + 64 * ASLOTS) <= 256 ? 256 : 512;
-static_assert(32 + 64 * ASLOTS <= 512, "TMEM holds 512 columns");
-constexpr uint32_t ACC_COL = 0;                     // 32 accumulator columns
-constexpr uint32_t ASLOT_COL0 = 32;                 // slot j: hi at 32+64j, lo at 32+64j+32
+constexpr int THREADS = 448;
+constexpr int WARP_EPI0 = 8, WARP_PROD = 12, WARP_MMA = 13;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t ACC_COL0 = 0;                    // 2 accumulator buffers x 32 columns
+constexpr uint32_t ASLOT_COL0 = 64;                 // group g, slot j: hi at 64 + (g*ASLOTS + j)*64, lo 32 further
+static_assert(64 + NGROUPS * ASLOTS * 64 <= 512, "TMEM holds 512 columns");
+static_assert(STAGES % NGROUPS == 0, "each transform group must always see the same stages");
 
 struct SmemLayout {
   // offsets from the 1024-aligned base
@@ -50,10 +55,20 @@ struct SmemLayout {
   static constexpr int at = y + STAGES * Y_STAGE_BYTES;
   static constexpr int apred = at + STAGES * AT_STAGE_BYTES;
   static constexpr int bars = apred + MAX_PRED * P * 4;
-  static constexpr int n_bars = 2 * STAGES + 2 * ASLOTS + 1;
+  static constexpr int n_bars = 2 * STAGES + 2 * NGROUPS * ASLOTS + 4;
   static constexpr int tmem_ptr = bars + n_bars * 8;
   static constexpr int total = tmem_ptr + 16;
 };
+
+__device__ __forceinline__ float dot16(const float* __restrict__ arow, const float (&g)[P], float s) {
+  const float4* ap = reinterpret_cast<const float4*>(arow);
+  const float4 a0 = ap[0], a1 = ap[1], a2 = ap[2], a3 = ap[3];
+  s = fmaf(a0.x, g[0], s);  s = fmaf(a0.y, g[1], s);  s = fmaf(a0.z, g[2], s);  s = fmaf(a0.w, g[3], s);
+  s = fmaf(a1.x, g[4], s);  s = fmaf(a1.y, g[5], s);  s = fmaf(a1.z, g[6], s);  s = fmaf(a1.w, g[7], s);
+  s = fmaf(a2.x, g[8], s);  s = fmaf(a2.y, g[9], s);  s = fmaf(a2.z, g[10], s); s = fmaf(a2.w, g[11], s);
+  s = fmaf(a3.x, g[12], s); s = fmaf(a3.y, g[13], s); s = fmaf(a3.z, g[14], s); s = fmaf(a3.w, g[15], s);
+  return s;
+}
 
 __global__ void __launch_bounds__(THREADS, 1)
 fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const FitArgs a,
@@ -67,39 +82,44 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
   const uint32_t s_bars = sbase + SmemLayout::bars;
   auto bar_full = [&](int s) { return s_bars + 8u * s; };
   auto bar_empty = [&](int s) { return s_bars + 8u * (STAGES + s); };
-  auto bar_afull = [&](int j) { return s_bars + 8u * (2 * STAGES + j); };
-  auto bar_aempty = [&](int j) { return s_bars + 8u * (2 * STAGES + ASLOTS + j); };
-  const uint32_t bar_acc = s_bars + 8u * (2 * STAGES + 2 * ASLOTS);
+  auto bar_afull = [&](int g, int j) { return s_bars + 8u * (2 * STAGES + g * ASLOTS + j); };
+  auto bar_aempty = [&](int g, int j) { return s_bars + 8u * (2 * STAGES + NGROUPS * ASLOTS + g * ASLOTS + j); };
+  auto bar_accfull = [&](int b) { return s_bars + 8u * (2 * STAGES + 2 * NGROUPS * ASLOTS + b); };
+  auto bar_accempty = [&](int b) { return s_bars + 8u * (2 * STAGES + 2 * NGROUPS * ASLOTS + 2 + b); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + SmemLayout::tmem_ptr);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   // ---- one-time setup
-  if (warp == 5) {
+  if (warp == WARP_MMA) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) {
         mbar_init(bar_full(s), 1);        // producer's expect_tx arrive (+ TMA bytes)
-        mbar_init(bar_empty(s), 5);       // 4 transform warps + 1 tcgen05.commit
+        mbar_init(bar_empty(s), 5);       // 4 warps of the consuming transform group + 1 tcgen05.commit
       }
-      for (int j = 0; j < ASLOTS; ++j) {
-        mbar_init(bar_afull(j), 4);       // 4 transform warps
-        mbar_init(bar_aempty(j), 1);      // tcgen05.commit
+      for (int g = 0; g < NGROUPS; ++g)
+        for (int j = 0; j < ASLOTS; ++j) {
+          mbar_init(bar_afull(g, j), 4);  // 4 transform warps
+          mbar_init(bar_aempty(g, j), 1); // tcgen05.commit
+        }
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(bar_accfull(b), 1);     // tcgen05.commit after the tile's last chunk
+        mbar_init(bar_accempty(b), 4);    // 4 epilogue warps have read the accumulators
       }
-      mbar_init(bar_acc, 1);
       fence_mbar_init();
     }
     __syncwarp();
     tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), TMEM_COLS);
     tmem_relinquish();
-  } else if (warp == 4) {
+  } else if (warp == WARP_PROD) {
     if (lane == 0) {
       prefetch_tensormap(tl.tmap_y);
       prefetch_tensormap(tl.tmap_at);
     }
-  } else {
+  } else if (warp >= WARP_EPI0 && warp < WARP_PROD) {
     // prediction rows of the whitened design -> shared (broadcast-read in the epilogue)
-    for (int i = threadIdx.x; i < a.n_pred * P; i += 128)
+    for (int i = threadIdx.x - WARP_EPI0 * 32; i < a.n_pred * P; i += 128)
       s_apred[i] = __ldg(d.apred + (size_t)a.pred_start * P + i);
   }
   tc_fence_before();
@@ -107,7 +127,7 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp == 4) {
+  if (warp == WARP_PROD) {
     // =========================== TMA producer ===========================
     // whole warp converged, one elected lane issues (keeps the tensor-map / barrier operands uniform)
     int stage = 0;
@@ -121,88 +141,128 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == WARP_MMA) {
     // =========================== MMA issuer ===========================
     // whole warp converged; tcgen05.mma / commit are predicated on elect.sync inside the wrappers
     constexpr uint32_t IDESC_N32 = umma_idesc_tf32(TILE_M, 2 * P);
     constexpr uint32_t IDESC_N16 = umma_idesc_tf32(TILE_M, P);
-    int stage = 0, aslot = 0;
-    uint32_t phase = 0, aphase = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    int stage = 0;
+    uint32_t phase = 0;
+    int aslot0 = 0, aslot1 = 0;
+    uint32_t aphase0 = 0u, aphase1 = 0u;
+    int grp = 0;                                     // chunk i of the CTA's stream belongs to group i & 1
+    int lt = 0;                                      // local tile counter -> accumulator buffer lt & 1
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+      const int ab = lt & 1;
+      mbar_wait(bar_accempty(ab), ((lt >> 1) & 1) ^ 1u);    // epilogue of tile lt-2 has drained this buffer
+      tc_fence_after();
+      const uint32_t d_acc = tmem_base + ACC_COL0 + ab * 32;
       for (int ch = 0; ch < n_chunks; ++ch) {
-        mbar_wait(bar_full(stage), phase);          // design chunk landed (same barrier as the y box)
-        mbar_wait(bar_afull(aslot), aphase);        // A operand written to TMEM by the transform warps
+        const int aslot = grp ? aslot1 : aslot0;
+        const uint32_t aphase = grp ? aphase1 : aphase0;
+        mbar_wait(bar_full(stage), phase);                 // design chunk landed (same barrier as the y box)
+        mbar_wait(bar_afull(grp, aslot), aphase);          // A operand written to TMEM by the transform group
         tc_fence_after();
         const uint64_t bdesc0 = umma_desc_k_sw128(s_at + stage * AT_STAGE_BYTES);
-        const uint32_t a_hi = tmem_base + ASLOT_COL0 + aslot * 64;
+        const uint32_t a_hi = tmem_base + ASLOT_COL0 + (grp * ASLOTS + aslot) * 64;
         const uint32_t a_lo = a_hi + 32;
 #pragma unroll
         for (int k = 0; k < KC / 8; ++k) {
           const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(k * 2);       // +32 B (16-B units)
-          umma_tf32_ts_elect(tmem_base + ACC_COL, a_hi + k * 8, bdesc, IDESC_N32, (ch | k) != 0 ? 1u : 0u);
-          umma_tf32_ts_elect(tmem_base + ACC_COL, a_lo + k * 8, bdesc, IDESC_N16, 1u);
+          umma_tf32_ts_elect(d_acc, a_hi + k * 8, bdesc, IDESC_N32, (ch | k) != 0 ? 1u : 0u);
+          umma_tf32_ts_elect(d_acc, a_lo + k * 8, bdesc, IDESC_N16, 1u);
         }
-        umma_commit_elect(bar_aempty(aslot));
+        umma_commit_elect(bar_aempty(grp, aslot));
         umma_commit_elect(bar_empty(stage));
-        if (ch == n_chunks - 1) umma_commit_elect(bar_acc);
+        if (ch == n_chunks - 1) umma_commit_elect(bar_accfull(ab));
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-        if (++aslot == ASLOTS) { aslot = 0; aphase ^= 1u; }
+        if (grp) { if (++aslot1 == ASLOTS) { aslot1 = 0; aphase1 ^= 1u; } }
+        else     { if (++aslot0 == ASLOTS) { aslot0 = 0; aphase0 ^= 1u; } }
+        grp ^= 1;
+      }
+    }
+  } else if (warp < NGROUPS * 4) {
+    // =========================== transform groups (warps 0-3, 4-7) ===========================
+    const int grp = warp >> 2;
+    const int r = threadIdx.x & 127;                    // row in tile == TMEM lane
+    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t row_off = static_cast<uint32_t>(r) * 128u;
+    const uint32_t sw = static_cast<uint32_t>(r & 7);
+    // this group's chunks are every other chunk of the CTA's stream
+    int stage = grp;                                    // STAGES is even: the group always sees stages of its parity
+    uint32_t phase = 0;
+    int aslot = 0;
+    uint32_t aphase = 0;
+    int tile = blockIdx.x;
+    int ch = grp;
+    while (ch >= n_chunks && tile < n_tiles) { ch -= n_chunks; tile += gridDim.x; }   // n_chunks == 1 corner
+    auto load_c = [&](int tl_) -> float {
+      const int64_t row = (int64_t)tl_ * TILE_M + r;
+      return (d.has_constant && tl_ < n_tiles && row < a.n) ? __ldg(a.y + row * a.ld_y) : 0.f;
+    };
+    float c = load_c(tile);
+    float c_next = load_c(tile + (int)gridDim.x);       // one tile ahead: the latency hides under the tile
+    while (tile < n_tiles) {
+      mbar_wait(bar_full(stage), phase);
+      const uint32_t rowp = s_y + stage * Y_STAGE_BYTES + row_off;
+      float4 v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = lds128(rowp + ((static_cast<uint32_t>(q) ^ sw) << 4));
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float e[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const float rr = e[w] - c;
+          const uint32_t h = __float_as_uint(rr) & 0xFFFFE000u;
+          hi[q * 4 + w] = h;
+          lo[q * 4 + w] = __float_as_uint(rr - __uint_as_float(h));
+        }
+      }
+      mbar_wait(bar_aempty(grp, aslot), aphase ^ 1u);   // MMAs that read this A slot have retired
+      tc_fence_after();
+      const uint32_t a_hi = tmem_base + lane_addr + ASLOT_COL0 + (grp * ASLOTS + aslot) * 64;
+      tmem_st_32x32b_x32(a_hi, hi);
+      tmem_st_32x32b_x32(a_hi + 32, lo);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar_afull(grp, aslot));
+        mbar_arrive(bar_empty(stage));                  // this warp's smem reads of the stage are done
+      }
+      stage += NGROUPS;
+      if (stage >= STAGES) { stage -= STAGES; phase ^= 1u; }
+      if (++aslot == ASLOTS) { aslot = 0; aphase ^= 1u; }
+      ch += NGROUPS;
+      while (ch >= n_chunks && tile < n_tiles) {        // next tile of this CTA
+        ch -= n_chunks;
+        tile += gridDim.x;
+        c = c_next;
+        c_next = load_c(tile + (int)gridDim.x);
       }
     }
   } else {
-    // =========================== transform + epilogue (warps 0-3) ===========================
-    const int r = threadIdx.x;                          // row in tile == TMEM lane
-    const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
-    const uint32_t row_off = static_cast<uint32_t>(r) * 128u;
-    const uint32_t sw = static_cast<uint32_t>(r & 7);
-    int stage = 0, aslot = 0;
-    uint32_t phase = 0, aphase = 0, accphase = 0;
+    // =========================== epilogue (warps 8-11) ===========================
+    const int r = threadIdx.x & 127;
+    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const bool vec_out = (a.n_pred % 4 == 0) && (a.ld_out % 4 == 0) &&
                          ((reinterpret_cast<uintptr_t>(a.out) & 15u) == 0);
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      float c = 0.f;
-      for (int ch = 0; ch < n_chunks; ++ch) {
-        mbar_wait(bar_full(stage), phase);
-        const uint32_t rowp = s_y + stage * Y_STAGE_BYTES + row_off;
-        float4 v[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = lds128(rowp + ((static_cast<uint32_t>(q) ^ sw) << 4));
-        if (ch == 0) c = d.has_constant ? v[0].x : 0.f;
-        uint32_t hi[32], lo[32];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float e[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
-#pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            const float rr = e[w] - c;
-            const uint32_t h = __float_as_uint(rr) & 0xFFFFE000u;
-            hi[q * 4 + w] = h;
-            lo[q * 4 + w] = __float_as_uint(rr - __uint_as_float(h));
-          }
-        }
-        mbar_wait(bar_aempty(aslot), aphase ^ 1u);      // MMAs that read this A slot have retired
-        tc_fence_after();
-        const uint32_t a_hi = tmem_base + lane_addr + ASLOT_COL0 + aslot * 64;
-        tmem_st_32x32b_x32(a_hi, hi);
-        tmem_st_32x32b_x32(a_hi + 32, lo);
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(bar_afull(aslot));
-          mbar_arrive(bar_empty(stage));                // this warp's smem reads of the stage are done
-        }
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-        if (++aslot == ASLOTS) { aslot = 0; aphase ^= 1u; }
-      }
-      // ---- epilogue: this thread's 16 moments -> forecast row
-      mbar_wait(bar_acc, accphase);
-      accphase ^= 1u;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+      const int ab = lt & 1;
+      const int64_t row = (int64_t)tile * TILE_M + r;
+      const bool live = row < a.n;
+      const float c = (d.has_constant && live) ? __ldg(a.y + row * a.ld_y) : 0.f;   // issued before the wait
+      mbar_wait(bar_accfull(ab), (lt >> 1) & 1);
       tc_fence_after();
       uint32_t acc[32];
-      tmem_ld_32x32b_x32(tmem_base + lane_addr + ACC_COL, acc);
+      tmem_ld_32x32b_x32(tmem_base + lane_addr + ACC_COL0 + ab * 32, acc);
       tmem_wait_ld();
       tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_accempty(ab));     // the MMA warp may overwrite this buffer now
       float g[P];
       bool finite = true;
 #pragma unroll
@@ -211,8 +271,6 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
         finite = finite && ((__float_as_uint(g[p]) & 0x7f800000u) != 0x7f800000u);
         if (!((d.kept_mask >> p) & 1u)) g[p] = 0.f;
       }
-      const int64_t row = (int64_t)tile * TILE_M + r;
-      const bool live = row < a.n;
       const bool pend = live && !finite;
       const unsigned pm = __ballot_sync(0xffffffffu, pend);
       if (lane == 0 && pm != 0u) atomicAdd(pending_count, __popc(pm));
@@ -223,29 +281,11 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
             for (int k = 0; k < a.n_pred; k += 4) {
               float o[4];
 #pragma unroll
-              for (int w = 0; w < 4; ++w) {
-                const float4* ap = reinterpret_cast<const float4*>(s_apred + (k + w) * P);
-                const float4 a0 = ap[0], a1 = ap[1], a2 = ap[2], a3 = ap[3];
-                float s = c;
-                s = fmaf(a0.x, g[0], s);  s = fmaf(a0.y, g[1], s);  s = fmaf(a0.z, g[2], s);  s = fmaf(a0.w, g[3], s);
-                s = fmaf(a1.x, g[4], s);  s = fmaf(a1.y, g[5], s);  s = fmaf(a1.z, g[6], s);  s = fmaf(a1.w, g[7], s);
-                s = fmaf(a2.x, g[8], s);  s = fmaf(a2.y, g[9], s);  s = fmaf(a2.z, g[10], s); s = fmaf(a2.w, g[11], s);
-                s = fmaf(a3.x, g[12], s); s = fmaf(a3.y, g[13], s); s = fmaf(a3.z, g[14], s); s = fmaf(a3.w, g[15], s);
-                o[w] = s;
-              }
+              for (int w = 0; w < 4; ++w) o[w] = dot16(s_apred + (k + w) * P, g, c);
               __stcs(reinterpret_cast<float4*>(outr + k), make_float4(o[0], o[1], o[2], o[3]));
             }
           } else {
-            for (int k = 0; k < a.n_pred; ++k) {
-              const float4* ap = reinterpret_cast<const float4*>(s_apred + k * P);
-              const float4 a0 = ap[0], a1 = ap[1], a2 = ap[2], a3 = ap[3];
-              float s = c;
-              s = fmaf(a0.x, g[0], s);  s = fmaf(a0.y, g[1], s);  s = fmaf(a0.z, g[2], s);  s = fmaf(a0.w, g[3], s);
-              s = fmaf(a1.x, g[4], s);  s = fmaf(a1.y, g[5], s);  s = fmaf(a1.z, g[6], s);  s = fmaf(a1.w, g[7], s);
-              s = fmaf(a2.x, g[8], s);  s = fmaf(a2.y, g[9], s);  s = fmaf(a2.z, g[10], s); s = fmaf(a2.w, g[11], s);
-              s = fmaf(a3.x, g[12], s); s = fmaf(a3.y, g[13], s); s = fmaf(a3.z, g[14], s); s = fmaf(a3.w, g[15], s);
-              outr[k] = s;
-            }
+            for (int k = 0; k < a.n_pred; ++k) outr[k] = dot16(s_apred + k * P, g, c);
           }
           if (a.out_beta != nullptr) {
             float* __restrict__ br = a.out_beta + row * P;
@@ -267,7 +307,7 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
   // ---- teardown
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == WARP_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
