@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--kernel", default="auto", choices=["auto", "warp", "tc"])
     ap.add_argument("--nan-frac", type=float, default=0.0)
     ap.add_argument("--e2e-series", type=int, default=0, help="series per e2e step (0 = same as --series)")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl", "multicast", "multicast-bulk"],
+                    help="N>1: how the forecast table reaches every rank: p2p = bulk stores from the fit kernel's epilogue "
+                         "into every peer's copy over NVLink (default), nccl = one all_gather after the kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-groups", type=int, default=0, help="groups per step of the reference arm (0 = 16 x cores)")
@@ -204,7 +207,18 @@ def run_ours(args):
     # ---- inputs: resident in HBM before the timed region; 4.4 GB per pass >> 126 MB L2
     y, start = mmf.synth.daily_store_item_demand_torch(n, t, seed=1234 + rank, nan_frac=args.nan_frac, device=dev)
     torch.cuda.synchronize()
-    table = torch.zeros((world * n, h), dtype=torch.float32, device=dev)        # the all-gathered forecast table
+    # the all-gathered forecast table.  N>1: NVLink symmetric memory so the fit kernel itself can store every
+    # forecast row into all ranks' copies (NVLS multicast or P2P); --gather nccl keeps the plain collective.
+    gather = "none"
+    sym = None
+    if world > 1 and args.gather != "nccl":
+        from mmf.sharding import SymmetricTable
+        sym = SymmetricTable(n, h, dev, mode=args.gather)
+        table = sym.table
+        gather = "fused-" + args.gather
+    else:
+        table = torch.zeros((world * n, h), dtype=torch.float32, device=dev)
+        gather = "nccl-all_gather" if world > 1 else "none"
     mine = table[rank * n:(rank + 1) * n]
 
     eng = mmf.ForecastEngine(device=local, kernel=args.kernel)
@@ -213,10 +227,21 @@ def run_ours(args):
     st = eng.fit_forecast(y, ps, npred, out=mine, want_stats=True)["stats"]
     launches_per_call, kernel_used = st.kernel_launches, st.kernel_used
 
+    def fit():
+        if sym is not None:
+            sym.fit_into(eng, y, ps, npred)             # forecasts land in every rank's table from the epilogue
+        else:
+            eng.fit_forecast(y, ps, npred, out=mine)
+
+    def exchange():
+        if sym is not None:
+            sym.barrier()                               # all peers' stores have landed
+        elif world > 1:
+            dist.all_gather_into_tensor(table, mine)    # in-place: mine is table's slice
+
     def step():
-        eng.fit_forecast(y, ps, npred, out=mine)
-        if world > 1:
-            dist.all_gather_into_tensor(table, mine)                            # in-place: mine is table's slice
+        fit()
+        exchange()
 
     for _ in range(W):
         step()
@@ -234,10 +259,9 @@ def run_ours(args):
     ev[0].record()
     for i in range(K):
         ev[2 + 2 * i].record()
-        eng.fit_forecast(y, ps, npred, out=mine)
+        fit()
         ev[3 + 2 * i].record()
-        if world > 1:
-            dist.all_gather_into_tensor(table, mine)
+        exchange()
     ev[1].record()
     torch.cuda.synchronize()
     if world > 1:
@@ -253,6 +277,16 @@ def run_ours(args):
     total_ms, kern_ms_avg = float(tt[0]), float(tt[1])
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     value = world * n * K / (total_ms * 1e-3)
+    gather_check = None
+    if world > 1:                                       # every rank's table must equal the NCCL-gathered one
+        ref = torch.empty((world * n, h), dtype=torch.float32, device=dev)
+        loc = torch.empty((n, h), dtype=torch.float32, device=dev)
+        eng.fit_forecast(y, ps, npred, out=loc)
+        dist.all_gather_into_tensor(ref, loc)
+        diff = (ref - table).abs().max().reshape(1)
+        dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+        gather_check = float(diff[0])
+        del ref, loc
 
     # ---- roofline of the dominant kernel (algorithmic bytes: 4*T read + 4*H written per series)
     peak, peak_src = peaks()
@@ -305,7 +339,8 @@ def run_ours(args):
                                        f"(BASELINE configs[3] shape; weak scaling)",
                            "series_per_gpu": n, "t": t, "horizon": h, "nan_frac": args.nan_frac,
                            "kernel": kernel_used, "l2": f"inputs {n * t * 4 / 1e9:.2f} GB per step per GPU > 126 MB L2",
-                           "parallelism": f"series-sharded x{world}" + (" + one NCCL all_gather of the forecast table" if world > 1 else "")},
+                           "parallelism": f"series-sharded x{world}" + (f" + forecast table replicated to every rank via {gather}" if world > 1 else ""),
+                           "gather": gather, "gather_max_abs_diff_vs_nccl": gather_check},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": launches_per_call * K, "clocks": clocks}
         print(json.dumps(line), flush=True)

@@ -39,6 +39,7 @@ constexpr int STAGES = MMF_TC_STAGES;  // shared-memory ring (20 KB per stage)
 constexpr int NGROUPS = 2;             // transform groups (alternate chunks)
 constexpr int ASLOTS = MMF_TC_ASLOTS;  // TMEM A-operand slots per transform group
 constexpr int MAX_PRED = 64;           // forecast rows the epilogue supports
+constexpr int BULK_MAX_PRED = 28;      // forecast rows the staged bulk-store epilogue supports (14 KB of smem)
 constexpr int Y_STAGE_BYTES = TILE_M * KC * 4;      // 16384
 constexpr int AT_STAGE_BYTES = 2 * P * KC * 4;      // 4096
 constexpr int THREADS = 448;
@@ -54,7 +55,8 @@ struct SmemLayout {
   static constexpr int y = 0;
   static constexpr int at = y + STAGES * Y_STAGE_BYTES;
   static constexpr int apred = at + STAGES * AT_STAGE_BYTES;
-  static constexpr int bars = apred + MAX_PRED * P * 4;
+  static constexpr int ostage = apred + MAX_PRED * P * 4;            // forecast tile staged for the bulk stores
+  static constexpr int bars = ostage + TILE_M * BULK_MAX_PRED * 4;
   static constexpr int n_bars = 2 * STAGES + 2 * NGROUPS * ASLOTS + 4;
   static constexpr int tmem_ptr = bars + n_bars * 8;
   static constexpr int total = tmem_ptr + 16;
@@ -79,6 +81,7 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
   const uint32_t s_y = sbase + SmemLayout::y;
   const uint32_t s_at = sbase + SmemLayout::at;
   float* s_apred = reinterpret_cast<float*>(smem + SmemLayout::apred);
+  float* s_ostage = reinterpret_cast<float*>(smem + SmemLayout::ostage);
   const uint32_t s_bars = sbase + SmemLayout::bars;
   auto bar_full = [&](int s) { return s_bars + 8u * s; };
   auto bar_empty = [&](int s) { return s_bars + 8u * (STAGES + s); };
@@ -247,8 +250,13 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
     // =========================== epilogue (warps 8-11) ===========================
     const int r = threadIdx.x & 127;
     const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const bool vec_out = (a.n_pred % 4 == 0) && (a.ld_out % 4 == 0) &&
-                         ((reinterpret_cast<uintptr_t>(a.out) & 15u) == 0);
+    bool vec_out = (a.n_pred % 4 == 0) && (a.ld_out % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15u) == 0);
+    for (int i = 0; i + 1 < a.n_out; ++i) vec_out = vec_out && ((reinterpret_cast<uintptr_t>(a.out_more[i]) & 15u) == 0);
+    // Staged epilogue: the tile's forecasts are one contiguous block of the table (rows are dense), so they are
+    // assembled in shared memory and leave as ONE bulk (TMA) store per destination -- full-size NVLink packets
+    // for the peers' copies instead of 16-B stores scattered at a 112-B stride.
+    const bool bulk = vec_out && a.out_multimem != 1 && a.ld_out == a.n_pred && a.n_pred <= BULK_MAX_PRED;
+    const uint32_t s_ostage_u32 = smem_u32(s_ostage);
     int lt = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
       const int ab = lt & 1;
@@ -274,19 +282,42 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
       const bool pend = live && !finite;
       const unsigned pm = __ballot_sync(0xffffffffu, pend);
       if (lane == 0 && pm != 0u) atomicAdd(pending_count, __popc(pm));
+      if (bulk) {
+        if (warp == WARP_EPI0) bulk_wait_read_elect();  // last tile's bulk stores no longer read the staging tile
+        named_bar_sync(1, 128);
+        float* __restrict__ srow = s_ostage + r * a.n_pred;
+        for (int k = 0; k < a.n_pred; k += 4) {          // PENDING rows stage garbage; the fix-up pass rewrites them
+          float o[4];
+#pragma unroll
+          for (int w = 0; w < 4; ++w) o[w] = dot16(s_apred + (k + w) * P, g, c);
+          *reinterpret_cast<float4*>(srow + k) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (warp == WARP_EPI0) {
+          const int64_t rows_here = (a.n - (int64_t)tile * TILE_M) < TILE_M ? (a.n - (int64_t)tile * TILE_M) : TILE_M;
+          const uint32_t bytes = static_cast<uint32_t>(rows_here) * a.n_pred * 4u;
+          const int64_t off = (int64_t)tile * TILE_M * a.n_pred;
+          bulk_store_elect(reinterpret_cast<uint64_t>(a.out + off), s_ostage_u32, bytes);
+          for (int i = 0; i + 1 < a.n_out; ++i)
+            bulk_store_elect(reinterpret_cast<uint64_t>(a.out_more[i] + off), s_ostage_u32, bytes);
+          bulk_commit_elect();
+        }
+      } else if (live && finite) {
+        const int64_t off = row * a.ld_out;
+        if (vec_out) {
+          for (int k = 0; k < a.n_pred; k += 4) {
+            float o[4];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) o[w] = dot16(s_apred + (k + w) * P, g, c);
+            store_out4(a, off + k, make_float4(o[0], o[1], o[2], o[3]));
+          }
+        } else {
+          for (int k = 0; k < a.n_pred; ++k) store_out1(a, off + k, dot16(s_apred + k * P, g, c));
+        }
+      }
       if (live) {
         if (finite) {
-          float* __restrict__ outr = a.out + row * a.ld_out;
-          if (vec_out) {
-            for (int k = 0; k < a.n_pred; k += 4) {
-              float o[4];
-#pragma unroll
-              for (int w = 0; w < 4; ++w) o[w] = dot16(s_apred + (k + w) * P, g, c);
-              __stcs(reinterpret_cast<float4*>(outr + k), make_float4(o[0], o[1], o[2], o[3]));
-            }
-          } else {
-            for (int k = 0; k < a.n_pred; ++k) outr[k] = dot16(s_apred + k * P, g, c);
-          }
           if (a.out_beta != nullptr) {
             float* __restrict__ br = a.out_beta + row * P;
             for (int p = 0; p < P; ++p) {
@@ -302,6 +333,7 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
         }
       }
     }
+    if (bulk && warp == WARP_EPI0) bulk_wait_all_elect();   // global writes complete before the kernel retires
   }
 
   // ---- teardown

@@ -363,7 +363,7 @@ fit_warp_kernel(const DesignView d, const FitArgs a, const int smem_rows) {
     }
 
     // ---- predictions for rows [pred_start, pred_start + n_pred): 4 series per design-row fetch
-    float* __restrict__ out0 = a.out + row0 * a.ld_out;
+    const int64_t off0 = row0 * a.ld_out;
 #pragma unroll 1
     for (int k = lane; k < a.n_pred; k += 32) {
       const int t = a.pred_start + k;
@@ -372,7 +372,7 @@ fit_warp_kernel(const DesignView d, const FitArgs a, const int smem_rows) {
       for (int s = 0; s < S; ++s) {
         if (act[s]) {
           const float yhat = any[s] ? dot16(a0, a1, a2, a3, acc[s], c[s]) : qnan;
-          __stcs(out0 + s * a.ld_out + k, yhat);
+          store_out1(a, off0 + s * a.ld_out + k, yhat);
         }
       }
     }

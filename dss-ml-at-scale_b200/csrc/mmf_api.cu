@@ -142,11 +142,13 @@ DesignView view_of(const Plan& p) {
 // Enqueue the fit for device-resident buffers on `s`.  status must be non-null.
 int run_device(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, int32_t pred_start, int32_t n_pred,
                float* out, int64_t ld_out, float* beta, int32_t* status, cudaStream_t s, int* launches,
-               int* kernel_used) {
+               int* kernel_used, float* const* out_more = nullptr, int n_out = 1, int multimem = 0) {
   const DesignView d = view_of(ctx->plan);
   FitArgs a{};
   a.y = y; a.n = n; a.ld_y = ld_y; a.pred_start = pred_start; a.n_pred = n_pred;
   a.out = out; a.ld_out = ld_out; a.out_beta = beta; a.status = status;
+  a.n_out = n_out; a.out_multimem = multimem;
+  for (int i = 0; i + 1 < n_out && i < MAX_OUT - 1; ++i) a.out_more[i] = out_more[i];
   a.only_pending = 0; a.pending_count = nullptr;
   const char* why = nullptr;
   int kernel = ctx->cfg.kernel;
@@ -522,6 +524,37 @@ int mmf_fit_forecast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, 
     stats->kernel_used = kernel_used;
   }
   return MMF_OK;
+}
+
+int mmf_fit_forecast_bcast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, int32_t pred_start,
+                               int32_t n_pred, const uint64_t* out_ptrs, int32_t n_out, int32_t multimem,
+                               int64_t ld_out, float* out_beta, int32_t* out_status) {
+  if (!ctx) return fail(MMF_E_INVALID, "ctx is NULL");
+  if (!ctx->plan.valid) return fail(MMF_E_NOPLAN, "mmf_plan_design has not been called");
+  const Plan& pl = ctx->plan;
+  if (n < 0 || (n > 0 && (!y || !out_ptrs))) return fail(MMF_E_INVALID, "bad y / out_ptrs / n");
+  if (n_out < 1 || n_out > MAX_OUT) return fail(MMF_E_INVALID, "n_out=%d outside [1,%d]", n_out, MAX_OUT);
+  if (multimem < 0 || multimem > 2) return fail(MMF_E_INVALID, "multimem must be 0, 1 (multimem.st) or 2 (bulk stores to the multicast address)");
+  if (multimem && n_out != 1) return fail(MMF_E_INVALID, "multimem=1 takes exactly one (multicast) pointer");
+  if (ld_y < pl.t_fit) return fail(MMF_E_INVALID, "ld_y=%lld < t_fit=%d", (long long)ld_y, pl.t_fit);
+  if (n_pred < 1 || pred_start < 0 || (int64_t)pred_start + n_pred > pl.n_rows)
+    return fail(MMF_E_INVALID, "prediction rows [%d,%d) outside the planned design (%d rows)", pred_start,
+                pred_start + n_pred, pl.n_rows);
+  if (ld_out < n_pred) return fail(MMF_E_INVALID, "ld_out=%lld < n_pred=%d", (long long)ld_out, n_pred);
+  if (n == 0) return MMF_OK;
+  CU_TRY(cudaSetDevice(ctx->device));
+  if (!is_device_ptr(y)) return fail(MMF_E_INVALID, "the broadcast variant takes device buffers only");
+  int32_t* status = out_status;
+  if (!status) {
+    int rc = grow((void**)&ctx->d_status_scratch, &ctx->status_scratch_cap, (size_t)n * sizeof(int32_t));
+    if (rc != MMF_OK) return rc;
+    status = ctx->d_status_scratch;
+  }
+  float* more[MAX_OUT - 1] = {};
+  for (int i = 1; i < n_out; ++i) more[i - 1] = reinterpret_cast<float*>(out_ptrs[i]);
+  int launches = 0, kernel_used = 0;
+  return run_device(ctx, y, n, ld_y, pred_start, n_pred, reinterpret_cast<float*>(out_ptrs[0]), ld_out, out_beta,
+                    status, ctx->stream, &launches, &kernel_used, more, n_out, multimem);
 }
 
 int mmf_alloc_pinned(size_t bytes, void** out) {

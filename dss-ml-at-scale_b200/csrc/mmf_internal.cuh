@@ -28,14 +28,19 @@ struct DesignView {
   int32_t has_constant;
 };
 
+constexpr int MAX_OUT = 8;               // replicas of the forecast table one launch can write (one per GPU)
+
 struct FitArgs {
   const float* y;
   int64_t n;
   int64_t ld_y;
   int32_t pred_start;
   int32_t n_pred;
-  float* out;
+  float* out;               // forecast rows [n, ld_out]; with n_out > 1 the same rows also go to out_more[]
   int64_t ld_out;
+  float* out_more[MAX_OUT - 1];   // peer-mapped copies of the table slice (NVLink P2P stores), n_out - 1 valid
+  int32_t n_out;            // 1 = local only
+  int32_t out_multimem;     // `out` is an NVLS multicast address: 1 -> multimem.st per row, 2 -> bulk (TMA) stores to it
   float* out_beta;          // nullable [n][P]
   int32_t* status;          // never null inside the library (scratch if caller passed NULL)
   int32_t only_pending;     // 1: process only rows whose status == MMF_STATUS_PENDING
@@ -54,5 +59,27 @@ struct TcLaunch {
 cudaError_t launch_fit_tc(const DesignView& d, const FitArgs& a, const TcLaunch& tl,
                           uint32_t* pending_count, int sm_count, cudaStream_t s);
 bool fit_tc_supported(const DesignView& d, const FitArgs& a, const char** why);
+
+#ifdef __CUDACC__
+// Forecast stores: plain, NVSwitch multicast (multimem.st) or fan-out over peer-mapped pointers.
+__device__ __forceinline__ void store_out1(const FitArgs& a, int64_t off, float v) {
+  if (a.out_multimem) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(a.out + off), "f"(v) : "memory");
+  } else {
+    __stcs(a.out + off, v);
+    for (int i = 0; i + 1 < a.n_out; ++i) __stcs(a.out_more[i] + off, v);
+  }
+}
+__device__ __forceinline__ void store_out4(const FitArgs& a, int64_t off, float4 v) {   // off: 16-B aligned element offset
+  if (a.out_multimem) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.out + off), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+  } else {
+    __stcs(reinterpret_cast<float4*>(a.out + off), v);
+    for (int i = 0; i + 1 < a.n_out; ++i) __stcs(reinterpret_cast<float4*>(a.out_more[i] + off), v);
+  }
+}
+#endif
 
 }  // namespace mmf

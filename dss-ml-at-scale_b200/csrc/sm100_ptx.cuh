@@ -101,6 +101,38 @@ __device__ __forceinline__ void tma_load_2d_elect(uint32_t bar, uint32_t tx_byte
       : "memory");
 }
 
+// bulk (TMA, non-tensor) store shared -> global of a contiguous block; warp-converged, one elected lane issues.
+// The destination may be local or a peer-mapped (NVLink) address.
+__device__ __forceinline__ void bulk_store_elect(uint64_t dst_global, uint32_t src_smem, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\t}"
+      ::"l"(dst_global), "r"(src_smem), "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit_elect() {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe cp.async.bulk.commit_group;\n\t}" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_elect() {       // the elected lane's pending bulk stores have read smem
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe cp.async.bulk.wait_group.read 0;\n\t}" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all_elect() {        // ... and have been written to global
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe cp.async.bulk.wait_group 0;\n\t}" ::: "memory");
+}
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ---- TMEM ------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {   // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)

@@ -218,6 +218,24 @@ class ForecastEngine:
         return res
 
 
+    def fit_forecast_bcast(self, y, pred_start: int, n_pred: int, out_ptrs, ld_out: int, multimem: int = 0,
+                           status=None):
+        """Fit the rows of the CUDA tensor ``y`` and store every forecast row to all ``out_ptrs``
+        (this GPU's slice first, then the peers' slices; or one NVLS multicast pointer with
+        ``multimem=True``) from inside the kernel.  Enqueue-only; see ``sharding.SymmetricTable``."""
+        import torch
+        if self.t_fit is None:
+            raise RuntimeError("plan()/plan_calendar() must be called first")
+        yp, n, t_have, ld_y = _describe(y, "y")
+        if not (_is_torch(y) and y.is_cuda and y.dtype == torch.float32) or t_have < self.t_fit:
+            raise ValueError("y must be a float32 CUDA tensor with at least t_fit columns")
+        self.set_stream(torch.cuda.current_stream(y.device).cuda_stream)
+        ptrs = (C.c_uint64 * len(out_ptrs))(*[int(p) for p in out_ptrs])
+        sp = _describe(status, "status")[0] if status is not None else None
+        N.check(self._lib.mmf_fit_forecast_bcast_f32(self._h, yp, n, ld_y, int(pred_start), int(n_pred), ptrs,
+                                                     len(out_ptrs), int(multimem), int(ld_out), None, sp))
+
+
 _default_engine: ForecastEngine | None = None
 
 

@@ -97,3 +97,42 @@ def forecast_packed_sharded(y_local, plan: ShardPlan, engine, pred_start: int, n
             engine.fit_forecast(y_local, pred_start, n_pred, out=buf[:n_local])
         local = torch.from_numpy(buf)
     return all_gather_table(local, plan, group)
+
+
+class SymmetricTable:
+    """The gathered forecast table ``[world * per, n_pred]`` in NVLink symmetric memory
+    (``torch.distributed._symmetric_memory``): every rank owns a full copy, peers' copies are mapped into
+    this process and -- when the fabric supports NVLS -- one multicast address reaches all of them.
+    ``ForecastEngine.fit_forecast_bcast`` then writes each forecast row into every copy from the fit
+    kernel's epilogue, so no separate all-gather runs; ``barrier()`` orders the reads."""
+
+    def __init__(self, per: int, n_pred: int, device, group=None, mode: str = "p2p"):
+        """mode: "p2p" (bulk stores to every peer copy, default), "multicast" (multimem.st to the NVLS
+        address) or "multicast-bulk" (bulk stores to the NVLS address)."""
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        group = group or dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.per, self.n_pred = per, n_pred
+        self.table = symm_mem.empty((self.world * per, n_pred), dtype=torch.float32, device=device)
+        self.table.zero_()
+        self.handle = symm_mem.rendezvous(self.table, group.group_name if hasattr(group, "group_name") else group)
+        slice_bytes = self.rank * per * n_pred * 4
+        mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+        if mode != "p2p" and not mc:
+            raise RuntimeError("no NVLS multicast address available for this group")
+        self.multimem = {"p2p": 0, "multicast": 1, "multicast-bulk": 2}[mode]
+        if self.multimem:
+            self.out_ptrs = [mc + slice_bytes]
+        else:                                             # own copy first, then the peers' (P2P stores)
+            order = [self.rank] + [r for r in range(self.world) if r != self.rank]
+            self.out_ptrs = [int(self.handle.buffer_ptrs[r]) + slice_bytes for r in order]
+
+    def barrier(self):
+        self.handle.barrier()
+
+    def fit_into(self, engine, y_local, pred_start: int, n_pred: int, status=None):
+        """Fit this rank's rows and broadcast their forecasts into every rank's table copy."""
+        engine.fit_forecast_bcast(y_local, pred_start, n_pred, self.out_ptrs, self.n_pred, self.multimem, status=status)

@@ -119,6 +119,19 @@ int mmf_fit_forecast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y,
                          float* out_pred, int64_t ld_out,
                          float* out_beta, int32_t* out_status, mmf_stats* stats);
 
+/* ---- multi-GPU: fit + write the forecast rows into every GPU's copy of the table ----------
+ * Same fit as above (device buffers only, enqueue-only), but each forecast row is stored to
+ * n_out destinations in ONE kernel: out_ptrs[0] is this GPU's own slice, out_ptrs[1..] the same slice
+ * of the peers' tables (peer-mapped pointers, NVLink P2P stores).  With multimem=1, n_out must be 1 and
+ * out_ptrs[0] is an NVLS multicast address: the kernel issues multimem.st and the NVSwitch replicates the
+ * store to every GPU.  The "single all-gather of the forecast table" (reference analogue: the shuffle
+ * back from the per-group tasks, 02:523-528) thereby rides under the fit; the caller only needs a
+ * cross-GPU barrier before reading peers' rows.                                                   */
+int mmf_fit_forecast_bcast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y,
+                               int32_t pred_start, int32_t n_pred,
+                               const uint64_t* out_ptrs, int32_t n_out, int32_t multimem, int64_t ld_out,
+                               float* out_beta, int32_t* out_status);
+
 /* ---- host memory helpers (Arrow buffers -> one cudaMemcpyAsync) ---------- */
 int mmf_alloc_pinned(size_t bytes, void** out);
 int mmf_free_pinned(void* p);

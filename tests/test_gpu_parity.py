@@ -276,3 +276,21 @@ def test_exog_only_design_on_gpu(engines):
     got = mmf.forecast_groups(df, design="exog_only")
     want = O.fanout_apply(df, lambda g: O.build_tune_and_score_model(g, design="exog_only"), ("Product", "SKU"))
     assert np.abs(got["Demand_Fitted"].to_numpy() - want["Demand_Fitted"].to_numpy()).max() <= tolerance(df["Demand"].to_numpy())
+
+
+def test_broadcast_stores_write_every_replica(engines):
+    """mmf_fit_forecast_bcast_f32 with plain device pointers: every forecast row lands in all replicas
+    (the NVLink P2P / multicast variants use the same store path with peer or multicast addresses)."""
+    import torch
+    y, start = mmf.synth.daily_store_item_demand(1000, 400, seed=21, nan_frac=0.0)
+    y[7, 10:20] = np.nan                                  # one row goes through the masked fix-up pass
+    yd = mmf.device_packed(y)
+    for k in ("auto", "warp"):
+        eng = engines[k]
+        _, ps, npred = eng.plan_calendar(start, 400, "D", 28, "future")
+        want = eng.fit_forecast(yd, ps, npred)
+        reps = [torch.zeros((1000, 28), device="cuda") for _ in range(3)]
+        eng.fit_forecast_bcast(yd, ps, npred, [r.data_ptr() for r in reps], 28)
+        torch.cuda.synchronize()
+        for r in reps:
+            assert torch.equal(r, want), k
