@@ -333,8 +333,9 @@ fit_warp_kernel(const DesignView d, const FitArgs a, const int smem_rows) {
 
     // ---- series with gaps: per-series normal equations (rare path, one copy of the code)
     int st[S];
+    bool deferred[S];
 #pragma unroll
-    for (int s = 0; s < S; ++s) st[s] = any[s] ? MMF_STATUS_OK : MMF_STATUS_EMPTY;
+    for (int s = 0; s < S; ++s) { st[s] = any[s] ? MMF_STATUS_OK : MMF_STATUS_EMPTY; deferred[s] = false; }
 #pragma unroll 1
     for (int s = 0; s < S; ++s) {
       bool need = false;
@@ -343,6 +344,30 @@ fit_warp_kernel(const DesignView d, const FitArgs a, const int smem_rows) {
       for (int q = 0; q < S; ++q)
         if (q == s) { need = act[q] && any[q] && miss[q] > 0; nm = miss[q]; }
       if (!need) continue;                          // warp-uniform
+      if (a.recs != nullptr && nm <= SOLVE_MISS_CAP && nm <= MISS_CAP && 2 * nm <= t_fit && t_fit <= 65535) {
+        // common case: hand the series to the thread-per-series solve kernel (moments + missing positions)
+        unsigned slot = 0;
+        if (lane == 0) slot = atomicAdd(a.rec_count, 1u);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot < a.rec_cap) {
+          SolveRec& rec = a.recs[slot];
+          float bl = 0.f, cs = 0.f;
+#pragma unroll
+          for (int q = 0; q < S; ++q) {
+            if (q == s) {
+              cs = c[q];
+#pragma unroll
+              for (int p = 0; p < P; ++p) bl = (lane == p) ? acc[q][p] : bl;
+            }
+          }
+          if (lane < P) rec.b[lane] = bl;
+          if (lane == P) { rec.c = cs; rec.nmiss = nm; a.rec_rows[slot] = row0 + s; }
+          for (int m = lane; m < nm; m += 32) rec.miss_t[m] = scr.miss_t[s][m];
+#pragma unroll
+          for (int q = 0; q < S; ++q) if (q == s) deferred[q] = true;
+          continue;
+        }
+      }
       float g[P];
 #pragma unroll
       for (int p = 0; p < P; ++p) {
@@ -370,7 +395,7 @@ fit_warp_kernel(const DesignView d, const FitArgs a, const int smem_rows) {
       const float4 a0 = A.vec(0, t), a1 = A.vec(1, t), a2 = A.vec(2, t), a3 = A.vec(3, t);
 #pragma unroll
       for (int s = 0; s < S; ++s) {
-        if (act[s]) {
+        if (act[s] && !deferred[s]) {
           const float yhat = any[s] ? dot16(a0, a1, a2, a3, acc[s], c[s]) : qnan;
           store_out1(a, off0 + s * a.ld_out + k, yhat);
         }
@@ -379,7 +404,7 @@ fit_warp_kernel(const DesignView d, const FitArgs a, const int smem_rows) {
     if (a.out_beta != nullptr && lane < P) {       // beta = W gamma (+ c on the intercept)
 #pragma unroll
       for (int s = 0; s < S; ++s) {
-        if (act[s]) {
+        if (act[s] && !deferred[s]) {
           float b = (lane == 0 && d.has_constant) ? c[s] : 0.f;
 #pragma unroll
           for (int q = 0; q < P; ++q) b = fmaf(__ldg(d.w + lane * P + q), acc[s][q], b);
@@ -390,7 +415,7 @@ fit_warp_kernel(const DesignView d, const FitArgs a, const int smem_rows) {
     if (lane == 0) {
 #pragma unroll
       for (int s = 0; s < S; ++s)
-        if (act[s]) a.status[row0 + s] = st[s];
+        if (act[s]) a.status[row0 + s] = deferred[s] ? MMF_STATUS_PENDING : st[s];
     }
   }
 }

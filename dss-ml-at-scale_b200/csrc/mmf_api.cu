@@ -100,7 +100,11 @@ struct mmf_ctx {
   bool own_stream = false;
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
-  uint32_t* d_pending = nullptr;
+  uint32_t* d_pending = nullptr;       // [0] rows the tcgen05 kernel left PENDING, [1] solve records written
+  SolveRec* d_recs = nullptr;          // deferred masked series (grown on demand, capped)
+  size_t recs_cap_bytes = 0;
+  int64_t* d_rec_rows = nullptr;
+  size_t rec_rows_cap_bytes = 0;
   int32_t* d_status_scratch = nullptr;
   size_t status_scratch_cap = 0;
   Plan plan;
@@ -155,24 +159,42 @@ int run_device(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, int32_t pr
   const bool tc_ok = fit_tc_supported(d, a, &why);
   if (kernel == MMF_KERNEL_TC && !tc_ok) return fail(MMF_E_UNSUPPORTED, "tcgen05 kernel not applicable: %s", why);
   if (kernel == MMF_KERNEL_AUTO) kernel = tc_ok ? MMF_KERNEL_TC : MMF_KERNEL_WARP;
+  const bool may_mask = !ctx->cfg.assume_finite;
+  if (may_mask) {
+    // scratch for the series with gaps: one 256-B record each, solved by solve_rows_kernel (capped at 4M records;
+    // overflow falls back to the warp-cooperative solve inside fit_warp_kernel)
+    const int64_t cap = std::min<int64_t>(n, 4 << 20);
+    int rc = grow((void**)&ctx->d_recs, &ctx->recs_cap_bytes, (size_t)cap * sizeof(SolveRec));
+    if (rc == MMF_OK) rc = grow((void**)&ctx->d_rec_rows, &ctx->rec_rows_cap_bytes, (size_t)cap * sizeof(int64_t));
+    if (rc != MMF_OK) return rc;
+    a.recs = ctx->d_recs;
+    a.rec_rows = ctx->d_rec_rows;
+    a.rec_count = ctx->d_pending + 1;
+    a.rec_cap = (uint32_t)cap;
+  }
+  CU_TRY(cudaMemsetAsync(ctx->d_pending, 0, 2 * sizeof(uint32_t), s));
   if (kernel == MMF_KERNEL_TC) {
     TcLaunch tl;
     int rc = encode_2d(tl.tmap_y, y, (uint64_t)d.t_fit, (uint64_t)n, (uint64_t)ld_y * 4, 32, 128);
     if (rc != MMF_OK) return rc;
     memcpy(tl.tmap_at, ctx->plan.tmap_at, 128);
-    CU_TRY(cudaMemsetAsync(ctx->d_pending, 0, sizeof(uint32_t), s));
     CU_TRY(launch_fit_tc(d, a, tl, ctx->d_pending, ctx->sm_count, s));
     ++*launches;
-    if (!ctx->cfg.assume_finite) {
+    if (may_mask) {
       FitArgs m = a;
       m.only_pending = 1;
       m.pending_count = ctx->d_pending;
       CU_TRY(launch_fit_warp(d, m, ctx->sm_count, s));
-      ++*launches;
+      CU_TRY(launch_solve_rows(d, m, ctx->sm_count, s));
+      *launches += 2;
     }
   } else {
     CU_TRY(launch_fit_warp(d, a, ctx->sm_count, s));
     ++*launches;
+    if (may_mask) {
+      CU_TRY(launch_solve_rows(d, a, ctx->sm_count, s));
+      ++*launches;
+    }
   }
   *kernel_used = kernel;
   return MMF_OK;
@@ -241,8 +263,8 @@ int mmf_create(const mmf_config* cfg, mmf_ctx** out) {
     cudaEventCreateWithFlags(&ctx->st[i].ev_comp, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->st[i].ev_d2h, cudaEventDisableTiming);
   }
-  if ((e = cudaMalloc(&ctx->d_pending, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
-  cudaMemset(ctx->d_pending, 0, sizeof(uint32_t));
+  if ((e = cudaMalloc(&ctx->d_pending, 2 * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
+  cudaMemset(ctx->d_pending, 0, 2 * sizeof(uint32_t));
   *out = ctx;
   return MMF_OK;
 }
@@ -260,6 +282,8 @@ int mmf_destroy(mmf_ctx* ctx) {
     if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
   }
   cudaFree(ctx->d_pending);
+  cudaFree(ctx->d_recs);
+  cudaFree(ctx->d_rec_rows);
   cudaFree(ctx->d_status_scratch);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);

@@ -28,6 +28,16 @@ struct DesignView {
   int32_t has_constant;
 };
 
+// One masked series handed from the streaming kernel to the thread-per-series solve kernel (256 B).
+constexpr int SOLVE_MISS_CAP = 92;
+struct SolveRec {
+  float b[P];                              // moments A_fit^T (y - c) over the observed rows
+  float c;                                 // centring constant
+  int32_t nmiss;                           // number of missing fit rows (<= SOLVE_MISS_CAP)
+  uint16_t miss_t[SOLVE_MISS_CAP];         // their grid positions
+};
+static_assert(sizeof(SolveRec) == 256, "SolveRec is one 256-B record");
+
 constexpr int MAX_OUT = 8;               // replicas of the forecast table one launch can write (one per GPU)
 
 struct FitArgs {
@@ -43,6 +53,10 @@ struct FitArgs {
   int32_t out_multimem;     // `out` is an NVLS multicast address: 1 -> multimem.st per row, 2 -> bulk (TMA) stores to it
   float* out_beta;          // nullable [n][P]
   int32_t* status;          // never null inside the library (scratch if caller passed NULL)
+  SolveRec* recs;           // nullable: masked rows are deferred to solve_rows_kernel through these records
+  int64_t* rec_rows;        //   row index of record i
+  uint32_t* rec_count;      //   number of records written (device counter)
+  uint32_t rec_cap;         //   capacity of recs / rec_rows
   int32_t only_pending;     // 1: process only rows whose status == MMF_STATUS_PENDING
   const uint32_t* pending_count;  // nullable; if non-null and *pending_count == 0 the kernel exits at once
 };
@@ -50,6 +64,10 @@ struct FitArgs {
 // warp-per-series CUDA-core kernel (general path)
 cudaError_t launch_fit_warp(const DesignView& d, const FitArgs& a, int sm_count, cudaStream_t s);
 size_t fit_warp_smem_bytes(const DesignView& d, int* smem_rows);
+
+// thread-per-series normal equations for the deferred masked rows: Gram downdate, in-order Cholesky with
+// pivot dropping and both triangular solves entirely in registers, then the forecasts
+cudaError_t launch_solve_rows(const DesignView& d, const FitArgs& a, int sm_count, cudaStream_t s);
 
 // TMA + tcgen05/TMEM kernel (fully observed fast path).  `tmap_y` / `tmap_at` are CUtensorMap blobs.
 struct TcLaunch {

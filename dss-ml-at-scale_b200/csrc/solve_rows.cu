@@ -1,0 +1,134 @@
+// solve_rows.cu -- thread-per-series normal equations for series with gaps.
+//
+// The streaming kernel (fit_warp.cu) leaves, for every masked series, a 256-B record: the moments
+// b = A_fit^T (y - c) over its observed rows, the centring constant and the grid positions of its missing
+// rows.  Here ONE THREAD owns one series and does the rest of build_tune_and_score_model's fit/predict
+// (reference 02:435-494) for it without touching shared memory or a barrier:
+//   G_i = diag(kept) - sum_{t missing} a_t a_t^T        136 packed entries, in registers
+//   in-order Cholesky of G_i with relative pivot dropping (MMF_PIVOT_TOL), fully unrolled
+//   L z = b, L^T gamma = z ; yhat_t = c + a_t . gamma ; beta = W gamma on request
+// A warp therefore factors 32 different 16x16 systems at once at full lane utilisation -- two orders of
+// magnitude fewer issue slots per series than a warp-cooperative Cholesky with a barrier per column.
+#include "mmf_internal.cuh"
+
+namespace mmf {
+namespace {
+
+constexpr int THREADS = 128;
+
+__device__ __forceinline__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }   // i >= j
+
+__global__ void __launch_bounds__(THREADS, 2)
+solve_rows_kernel(const DesignView d, const FitArgs a) {
+  const uint32_t count = min(*a.rec_count, a.rec_cap);
+  for (uint32_t i = blockIdx.x * THREADS + threadIdx.x; i < count; i += gridDim.x * THREADS) {
+    const SolveRec& rec = a.recs[i];
+    const int64_t row = a.rec_rows[i];
+    float b[P];
+    {
+      const float4* bp = reinterpret_cast<const float4*>(rec.b);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 v = bp[q];
+        b[4 * q] = v.x; b[4 * q + 1] = v.y; b[4 * q + 2] = v.z; b[4 * q + 3] = v.w;
+      }
+    }
+    const float c = rec.c;
+    const int nmiss = rec.nmiss;
+
+    // ---- G_i = diag(kept) - sum over the missing rows of a_t a_t^T
+    float G[NPAIR];
+#pragma unroll
+    for (int e = 0; e < NPAIR; ++e) G[e] = 0.f;
+#pragma unroll
+    for (int j = 0; j < P; ++j) G[tri(j, j)] = ((d.kept_mask >> j) & 1u) ? 1.f : 0.f;
+#pragma unroll 1
+    for (int m = 0; m < nmiss; ++m) {
+      const int t = rec.miss_t[m];
+      const float4* ap = reinterpret_cast<const float4*>(d.apred + (size_t)t * P);
+      const float4 a0 = __ldg(ap), a1 = __ldg(ap + 1), a2 = __ldg(ap + 2), a3 = __ldg(ap + 3);
+      const float av[P] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
+#pragma unroll
+      for (int r = 0; r < P; ++r)
+#pragma unroll
+        for (int q = 0; q <= r; ++q) G[tri(r, q)] = fmaf(-av[r], av[q], G[tri(r, q)]);
+    }
+
+    // ---- in-order right-looking Cholesky with pivot dropping (dropped column: L_jj = 1, rest 0)
+    unsigned outmask = ~d.kept_mask & 0xFFFFu;
+    unsigned dropped = 0u;
+    float diag0[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) diag0[j] = G[tri(j, j)];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const float dj = G[tri(j, j)];
+      const bool kept_cal = (d.kept_mask >> j) & 1u;
+      const bool keep = kept_cal && diag0[j] > 0.f && dj > MMF_PIVOT_TOL * diag0[j];
+      if (!keep) {
+        outmask |= 1u << j;
+        if (kept_cal && diag0[j] > 0.f) dropped |= 1u << j;
+      }
+      const float inv = keep ? rsqrtf(dj) : 0.f;
+      G[tri(j, j)] = keep ? dj * inv : 1.f;
+#pragma unroll
+      for (int r = j + 1; r < P; ++r) G[tri(r, j)] *= inv;             // column j of L (zero when dropped)
+#pragma unroll
+      for (int r = j + 1; r < P; ++r)
+#pragma unroll
+        for (int q = j + 1; q <= r; ++q) G[tri(r, q)] = fmaf(-G[tri(r, j)], G[tri(q, j)], G[tri(r, q)]);
+    }
+    // ---- L z = b, L^T gamma = z (dropped columns pinned to 0)
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      float s = b[j];
+#pragma unroll
+      for (int q = 0; q < j; ++q) s = fmaf(-G[tri(j, q)], b[q], s);
+      b[j] = ((outmask >> j) & 1u) ? 0.f : s / G[tri(j, j)];
+    }
+#pragma unroll
+    for (int j = P - 1; j >= 0; --j) {
+      float s = b[j];
+#pragma unroll
+      for (int r = j + 1; r < P; ++r) s = fmaf(-G[tri(r, j)], b[r], s);
+      b[j] = ((outmask >> j) & 1u) ? 0.f : s / G[tri(j, j)];
+    }
+
+    // ---- forecasts
+    const int64_t off = row * a.ld_out;
+#pragma unroll 1
+    for (int k = 0; k < a.n_pred; ++k) {
+      const float4* ap = reinterpret_cast<const float4*>(d.apred + (size_t)(a.pred_start + k) * P);
+      const float4 a0 = __ldg(ap), a1 = __ldg(ap + 1), a2 = __ldg(ap + 2), a3 = __ldg(ap + 3);
+      float s = c;
+      s = fmaf(a0.x, b[0], s);  s = fmaf(a0.y, b[1], s);  s = fmaf(a0.z, b[2], s);  s = fmaf(a0.w, b[3], s);
+      s = fmaf(a1.x, b[4], s);  s = fmaf(a1.y, b[5], s);  s = fmaf(a1.z, b[6], s);  s = fmaf(a1.w, b[7], s);
+      s = fmaf(a2.x, b[8], s);  s = fmaf(a2.y, b[9], s);  s = fmaf(a2.z, b[10], s); s = fmaf(a2.w, b[11], s);
+      s = fmaf(a3.x, b[12], s); s = fmaf(a3.y, b[13], s); s = fmaf(a3.z, b[14], s); s = fmaf(a3.w, b[15], s);
+      store_out1(a, off + k, s);
+    }
+    if (a.out_beta != nullptr) {
+#pragma unroll 1
+      for (int p = 0; p < P; ++p) {
+        float s = (p == 0 && d.has_constant) ? c : 0.f;
+#pragma unroll
+        for (int q = 0; q < P; ++q) s = fmaf(__ldg(d.w + p * P + q), b[q], s);
+        a.out_beta[row * P + p] = s;
+      }
+    }
+    a.status[row] = dropped ? MMF_STATUS_RANKDEF : MMF_STATUS_OK;
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_solve_rows(const DesignView& d, const FitArgs& a, int sm_count, cudaStream_t s) {
+  if (a.recs == nullptr || a.rec_cap == 0) return cudaSuccess;
+  const int64_t want = ((int64_t)a.rec_cap + THREADS - 1) / THREADS;
+  const int64_t cap = (int64_t)sm_count * 8;
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
+  solve_rows_kernel<<<grid, THREADS, 0, s>>>(d, a);
+  return cudaGetLastError();
+}
+
+}  // namespace mmf
