@@ -39,6 +39,7 @@ constexpr int STAGES = MMF_TC_STAGES;  // shared-memory ring (20 KB per stage)
 constexpr int NGROUPS = 2;             // transform groups (alternate chunks)
 constexpr int ASLOTS = MMF_TC_ASLOTS;  // TMEM A-operand slots per transform group
 constexpr int MAX_PRED = 64;           // forecast rows the epilogue supports
+constexpr int NM_RING = 8;             // tiles the transform groups may run ahead of the epilogue (2 slots x 2 groups)
 constexpr int BULK_MAX_PRED = 28;      // forecast rows the staged bulk-store epilogue supports (14 KB of smem)
 constexpr int Y_STAGE_BYTES = TILE_M * KC * 4;      // 16384
 constexpr int AT_STAGE_BYTES = 2 * P * KC * 4;      // 4096
@@ -56,7 +57,8 @@ struct SmemLayout {
   static constexpr int at = y + STAGES * Y_STAGE_BYTES;
   static constexpr int apred = at + STAGES * AT_STAGE_BYTES;
   static constexpr int ostage = apred + MAX_PRED * P * 4;            // forecast tile staged for the bulk stores
-  static constexpr int bars = ostage + TILE_M * BULK_MAX_PRED * 4;
+  static constexpr int nm = ostage + TILE_M * BULK_MAX_PRED * 4;     // per-row missing counts: [NM_RING][2 groups][128] u16
+  static constexpr int bars = nm + NM_RING * NGROUPS * TILE_M * 2;
   static constexpr int n_bars = 2 * STAGES + 2 * NGROUPS * ASLOTS + 4;
   static constexpr int tmem_ptr = bars + n_bars * 8;
   static constexpr int total = tmem_ptr + 16;
@@ -82,6 +84,10 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
   const uint32_t s_at = sbase + SmemLayout::at;
   float* s_apred = reinterpret_cast<float*>(smem + SmemLayout::apred);
   float* s_ostage = reinterpret_cast<float*>(smem + SmemLayout::ostage);
+  uint16_t* s_nm = reinterpret_cast<uint16_t*>(smem + SmemLayout::nm);
+  // series with gaps: substitute the centring constant for missing values (so the moments stay exact), record
+  // where they were, and let the epilogue queue a SolveRec for solve_rows_kernel instead of a second pass
+  const bool collect = a.recs != nullptr && d.t_fit <= 65535;
   const uint32_t s_bars = sbase + SmemLayout::bars;
   auto bar_full = [&](int s) { return s_bars + 8u * s; };
   auto bar_empty = [&](int s) { return s_bars + 8u * (STAGES + s); };
@@ -203,14 +209,46 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
       const int64_t row = (int64_t)tl_ * TILE_M + r;
       return (d.has_constant && tl_ < n_tiles && row < a.n) ? __ldg(a.y + row * a.ld_y) : 0.f;
     };
+    auto finite = [](float x) { return (__float_as_uint(x) & 0x7f800000u) != 0x7f800000u; };
     float c = load_c(tile);
     float c_next = load_c(tile + (int)gridDim.x);       // one tile ahead: the latency hides under the tile
+    bool bad = collect && !finite(c);                   // cannot centre on a missing first value: general path
+    if (bad) c = 0.f;
+    int nm = 0;                                         // missing values this thread saw in the current tile
+    int lt = 0;                                         // local tile counter (s_nm ring slot)
     while (tile < n_tiles) {
       mbar_wait(bar_full(stage), phase);
       const uint32_t rowp = s_y + stage * Y_STAGE_BYTES + row_off;
       float4 v[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) v[q] = lds128(rowp + ((static_cast<uint32_t>(q) ^ sw) << 4));
+      if (collect) {
+        float chk = 0.f;                                // 0 * x is NaN exactly when x is NaN or Inf
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          chk = fmaf(v[q].x, 0.f, chk); chk = fmaf(v[q].y, 0.f, chk);
+          chk = fmaf(v[q].z, 0.f, chk); chk = fmaf(v[q].w, 0.f, chk);
+        }
+        if (!(chk == 0.f)) {                            // rare: this row has a gap inside this chunk
+          // branch-free substitution + a bit mask of the gap positions, then a short loop over the set bits
+          unsigned gaps = 0u;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const bool f0 = finite(v[q].x), f1 = finite(v[q].y), f2 = finite(v[q].z), f3 = finite(v[q].w);
+            gaps |= (f0 ? 0u : 1u << (4 * q)) | (f1 ? 0u : 2u << (4 * q)) | (f2 ? 0u : 4u << (4 * q)) | (f3 ? 0u : 8u << (4 * q));
+            v[q].x = f0 ? v[q].x : c;  v[q].y = f1 ? v[q].y : c;      // contributes (c - c) = 0 to every moment
+            v[q].z = f2 ? v[q].z : c;  v[q].w = f3 ? v[q].w : c;
+          }
+          uint16_t* __restrict__ mt = a.recs[(int64_t)tile * TILE_M + r].miss_t + grp * SOLVE_SEG;
+          const int tbase = ch * KC;
+          while (gaps) {
+            const int pos = __ffs(gaps) - 1;
+            gaps &= gaps - 1u;
+            if (nm < SOLVE_SEG) mt[nm] = static_cast<uint16_t>(tbase + pos);
+            ++nm;
+          }
+        }
+      }
       uint32_t hi[32], lo[32];
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -228,6 +266,10 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
       const uint32_t a_hi = tmem_base + lane_addr + ASLOT_COL0 + (grp * ASLOTS + aslot) * 64;
       tmem_st_32x32b_x32(a_hi, hi);
       tmem_st_32x32b_x32(a_hi + 32, lo);
+      if (collect && ch + NGROUPS >= n_chunks) {        // my last chunk of this tile: publish the count (the arrive releases it)
+        const int cnt = nm > 0x7ffe ? 0x7ffe : nm;
+        s_nm[((lt & (NM_RING - 1)) * NGROUPS + grp) * TILE_M + r] = static_cast<uint16_t>(cnt | (bad ? 0x8000 : 0));
+      }
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
@@ -242,8 +284,12 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
       while (ch >= n_chunks && tile < n_tiles) {        // next tile of this CTA
         ch -= n_chunks;
         tile += gridDim.x;
+        ++lt;
+        nm = 0;
         c = c_next;
         c_next = load_c(tile + (int)gridDim.x);
+        bad = collect && !finite(c);
+        if (bad) c = 0.f;
       }
     }
   } else {
@@ -262,11 +308,23 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
       const int ab = lt & 1;
       const int64_t row = (int64_t)tile * TILE_M + r;
       const bool live = row < a.n;
-      const float c = (d.has_constant && live) ? __ldg(a.y + row * a.ld_y) : 0.f;   // issued before the wait
+      float c = (d.has_constant && live) ? __ldg(a.y + row * a.ld_y) : 0.f;   // issued before the wait
       mbar_wait(bar_accfull(ab), (lt >> 1) & 1);
       tc_fence_after();
       uint32_t acc[32];
       tmem_ld_32x32b_x32(tmem_base + lane_addr + ACC_COL0 + ab * 32, acc);
+      // gaps seen by the two transform groups in this tile (a group owns no chunk of it only when n_chunks == 1)
+      int nm0 = 0, nm1 = 0;
+      bool general = false;
+      if (collect) {
+        const uint16_t* nmrow = s_nm + (lt & (NM_RING - 1)) * NGROUPS * TILE_M + r;
+        const bool has0 = n_chunks >= 2 || ((lt * n_chunks) & 1) == 0;
+        const bool has1 = n_chunks >= 2 || ((lt * n_chunks) & 1) == 1;
+        const unsigned f0 = has0 ? nmrow[0] : 0u, f1 = has1 ? nmrow[TILE_M] : 0u;
+        nm0 = f0 & 0x7fff; nm1 = f1 & 0x7fff;
+        general = ((f0 | f1) & 0x8000u) != 0u || nm0 > SOLVE_SEG || nm1 > SOLVE_SEG;
+        if (general) c = 0.f;
+      }
       tmem_wait_ld();
       tc_fence_before();
       __syncwarp();
@@ -279,9 +337,26 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
         finite = finite && ((__float_as_uint(g[p]) & 0x7f800000u) != 0x7f800000u);
         if (!((d.kept_mask >> p) & 1u)) g[p] = 0.f;
       }
-      const bool pend = live && !finite;
+      const bool pend = live && (!finite || general);            // -> general warp pass
+      const bool defer = live && !pend && (nm0 + nm1) > 0;       // -> thread-per-series solve of the queued record
       const unsigned pm = __ballot_sync(0xffffffffu, pend);
       if (lane == 0 && pm != 0u) atomicAdd(pending_count, __popc(pm));
+      const unsigned dm = __ballot_sync(0xffffffffu, defer);
+      if (dm != 0u) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(a.rec_count, __popc(dm));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (defer) {
+          SolveRec& rec = a.recs[row];
+          float4* bp = reinterpret_cast<float4*>(rec.b);
+          bp[0] = make_float4(g[0], g[1], g[2], g[3]);    bp[1] = make_float4(g[4], g[5], g[6], g[7]);
+          bp[2] = make_float4(g[8], g[9], g[10], g[11]);  bp[3] = make_float4(g[12], g[13], g[14], g[15]);
+          rec.c = c;
+          rec.nm[0] = static_cast<uint16_t>(nm0);
+          rec.nm[1] = static_cast<uint16_t>(nm1);
+          a.rec_rows[base + __popc(dm & ((1u << lane) - 1u))] = row;
+        }
+      }
       if (bulk) {
         if (warp == WARP_EPI0) bulk_wait_read_elect();  // last tile's bulk stores no longer read the staging tile
         named_bar_sync(1, 128);
@@ -303,7 +378,7 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
             bulk_store_elect(reinterpret_cast<uint64_t>(a.out_more[i] + off), s_ostage_u32, bytes);
           bulk_commit_elect();
         }
-      } else if (live && finite) {
+      } else if (live && !pend && !defer) {
         const int64_t off = row * a.ld_out;
         if (vec_out) {
           for (int k = 0; k < a.n_pred; k += 4) {
@@ -317,7 +392,7 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
         }
       }
       if (live) {
-        if (finite) {
+        if (!pend && !defer) {
           if (a.out_beta != nullptr) {
             float* __restrict__ br = a.out_beta + row * P;
             for (int p = 0; p < P; ++p) {
@@ -329,7 +404,7 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
           }
           a.status[row] = MMF_STATUS_OK;
         } else {
-          a.status[row] = MMF_STATUS_PENDING;
+          a.status[row] = pend ? MMF_STATUS_PENDING : MMF_STATUS_DEFERRED;
         }
       }
     }

@@ -346,27 +346,27 @@ fit_warp_kernel(const DesignView d, const FitArgs a, const int smem_rows) {
       if (!need) continue;                          // warp-uniform
       if (a.recs != nullptr && nm <= SOLVE_MISS_CAP && nm <= MISS_CAP && 2 * nm <= t_fit && t_fit <= 65535) {
         // common case: hand the series to the thread-per-series solve kernel (moments + missing positions)
-        unsigned slot = 0;
-        if (lane == 0) slot = atomicAdd(a.rec_count, 1u);
-        slot = __shfl_sync(0xffffffffu, slot, 0);
-        if (slot < a.rec_cap) {
-          SolveRec& rec = a.recs[slot];
-          float bl = 0.f, cs = 0.f;
+        SolveRec& rec = a.recs[row0 + s];
+        float bl = 0.f, cs = 0.f;
 #pragma unroll
-          for (int q = 0; q < S; ++q) {
-            if (q == s) {
-              cs = c[q];
+        for (int q = 0; q < S; ++q) {
+          if (q == s) {
+            cs = c[q];
 #pragma unroll
-              for (int p = 0; p < P; ++p) bl = (lane == p) ? acc[q][p] : bl;
-            }
+            for (int p = 0; p < P; ++p) bl = (lane == p) ? acc[q][p] : bl;
           }
-          if (lane < P) rec.b[lane] = bl;
-          if (lane == P) { rec.c = cs; rec.nmiss = nm; a.rec_rows[slot] = row0 + s; }
-          for (int m = lane; m < nm; m += 32) rec.miss_t[m] = scr.miss_t[s][m];
-#pragma unroll
-          for (int q = 0; q < S; ++q) if (q == s) deferred[q] = true;
-          continue;
         }
+        if (lane < P) rec.b[lane] = bl;
+        if (lane == P) {
+          rec.c = cs;
+          rec.nm[0] = (uint16_t)(nm < SOLVE_SEG ? nm : SOLVE_SEG);
+          rec.nm[1] = (uint16_t)(nm < SOLVE_SEG ? 0 : nm - SOLVE_SEG);
+          a.rec_rows[atomicAdd(a.rec_count, 1u)] = row0 + s;
+        }
+        for (int m = lane; m < nm; m += 32) rec.miss_t[m] = scr.miss_t[s][m];   // segment 1 starts at SOLVE_SEG
+#pragma unroll
+        for (int q = 0; q < S; ++q) if (q == s) deferred[q] = true;
+        continue;
       }
       float g[P];
 #pragma unroll
@@ -415,7 +415,7 @@ fit_warp_kernel(const DesignView d, const FitArgs a, const int smem_rows) {
     if (lane == 0) {
 #pragma unroll
       for (int s = 0; s < S; ++s)
-        if (act[s]) a.status[row0 + s] = deferred[s] ? MMF_STATUS_PENDING : st[s];
+        if (act[s]) a.status[row0 + s] = deferred[s] ? MMF_STATUS_DEFERRED : st[s];
     }
   }
 }

@@ -161,9 +161,9 @@ int run_device(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, int32_t pr
   if (kernel == MMF_KERNEL_AUTO) kernel = tc_ok ? MMF_KERNEL_TC : MMF_KERNEL_WARP;
   const bool may_mask = !ctx->cfg.assume_finite;
   if (may_mask) {
-    // scratch for the series with gaps: one 256-B record each, solved by solve_rows_kernel (capped at 4M records;
-    // overflow falls back to the warp-cooperative solve inside fit_warp_kernel)
-    const int64_t cap = std::min<int64_t>(n, 4 << 20);
+    // scratch for the series with gaps: one 256-B record per row (filled only for rows that have gaps) and the
+    // work list of rows whose record is ready for solve_rows_kernel
+    const int64_t cap = n;
     int rc = grow((void**)&ctx->d_recs, &ctx->recs_cap_bytes, (size_t)cap * sizeof(SolveRec));
     if (rc == MMF_OK) rc = grow((void**)&ctx->d_rec_rows, &ctx->rec_rows_cap_bytes, (size_t)cap * sizeof(int64_t));
     if (rc != MMF_OK) return rc;

@@ -28,15 +28,19 @@ struct DesignView {
   int32_t has_constant;
 };
 
-// One masked series handed from the streaming kernel to the thread-per-series solve kernel (256 B).
-constexpr int SOLVE_MISS_CAP = 92;
+// One series with gaps, handed to the thread-per-series solve kernel (256 B, indexed by row).
+// Missing grid positions come in two segments so that two producers (the two transform groups of the
+// tcgen05 kernel) can append without atomics: segment g holds nm[g] entries at miss_t[g*SOLVE_SEG ...].
+constexpr int SOLVE_SEG = 46;
+constexpr int SOLVE_MISS_CAP = 2 * SOLVE_SEG;
 struct SolveRec {
   float b[P];                              // moments A_fit^T (y - c) over the observed rows
   float c;                                 // centring constant
-  int32_t nmiss;                           // number of missing fit rows (<= SOLVE_MISS_CAP)
-  uint16_t miss_t[SOLVE_MISS_CAP];         // their grid positions
+  uint16_t nm[2];                          // entries in each segment
+  uint16_t miss_t[SOLVE_MISS_CAP];         // grid positions of the missing fit rows
 };
 static_assert(sizeof(SolveRec) == 256, "SolveRec is one 256-B record");
+constexpr int MMF_STATUS_DEFERRED = -2;    // internal: the row's SolveRec is queued for solve_rows_kernel
 
 constexpr int MAX_OUT = 8;               // replicas of the forecast table one launch can write (one per GPU)
 
@@ -53,10 +57,10 @@ struct FitArgs {
   int32_t out_multimem;     // `out` is an NVLS multicast address: 1 -> multimem.st per row, 2 -> bulk (TMA) stores to it
   float* out_beta;          // nullable [n][P]
   int32_t* status;          // never null inside the library (scratch if caller passed NULL)
-  SolveRec* recs;           // nullable: masked rows are deferred to solve_rows_kernel through these records
-  int64_t* rec_rows;        //   row index of record i
-  uint32_t* rec_count;      //   number of records written (device counter)
-  uint32_t rec_cap;         //   capacity of recs / rec_rows
+  SolveRec* recs;           // nullable: [n] records by row; series with gaps are deferred to solve_rows_kernel
+  int64_t* rec_rows;        //   [n] work list: rows whose record is ready
+  uint32_t* rec_count;      //   length of the work list (device counter)
+  uint32_t rec_cap;         //   == n
   int32_t only_pending;     // 1: process only rows whose status == MMF_STATUS_PENDING
   const uint32_t* pending_count;  // nullable; if non-null and *pending_count == 0 the kernel exits at once
 };

@@ -22,8 +22,8 @@ __global__ void __launch_bounds__(THREADS, 2)
 solve_rows_kernel(const DesignView d, const FitArgs a) {
   const uint32_t count = min(*a.rec_count, a.rec_cap);
   for (uint32_t i = blockIdx.x * THREADS + threadIdx.x; i < count; i += gridDim.x * THREADS) {
-    const SolveRec& rec = a.recs[i];
     const int64_t row = a.rec_rows[i];
+    const SolveRec& rec = a.recs[row];
     float b[P];
     {
       const float4* bp = reinterpret_cast<const float4*>(rec.b);
@@ -34,7 +34,7 @@ solve_rows_kernel(const DesignView d, const FitArgs a) {
       }
     }
     const float c = rec.c;
-    const int nmiss = rec.nmiss;
+    const int nm0 = rec.nm[0], nm1 = rec.nm[1];
 
     // ---- G_i = diag(kept) - sum over the missing rows of a_t a_t^T
     float G[NPAIR];
@@ -43,8 +43,8 @@ solve_rows_kernel(const DesignView d, const FitArgs a) {
 #pragma unroll
     for (int j = 0; j < P; ++j) G[tri(j, j)] = ((d.kept_mask >> j) & 1u) ? 1.f : 0.f;
 #pragma unroll 1
-    for (int m = 0; m < nmiss; ++m) {
-      const int t = rec.miss_t[m];
+    for (int m = 0; m < nm0 + nm1; ++m) {
+      const int t = rec.miss_t[m < nm0 ? m : SOLVE_SEG + (m - nm0)];
       const float4* ap = reinterpret_cast<const float4*>(d.apred + (size_t)t * P);
       const float4 a0 = __ldg(ap), a1 = __ldg(ap + 1), a2 = __ldg(ap + 2), a3 = __ldg(ap + 3);
       const float av[P] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};

@@ -108,7 +108,9 @@ def test_parity_masked_series(engines, kernel):
     assert (np.abs(pred - want).max(axis=1) <= tol).all()
     assert np.array_equal(status, wst)
     if kernel != "warp":
-        assert res["stats"].n_pending == 300
+        # rows whose first value is missing (or with > 46 gaps per transform group) take the general pass;
+        # every other gappy row is solved from the record the tcgen05 kernel queued
+        assert 0 < res["stats"].n_pending < 300
 
 
 def _design(start, t, h):
