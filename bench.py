@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--horizon", type=int, default=28)
     ap.add_argument("--kernel", default="auto", choices=["auto", "warp", "tc"])
     ap.add_argument("--nan-frac", type=float, default=0.0)
+    ap.add_argument("--mode", default="future", choices=["future", "holdout"],
+                    help="future: fit all T rows, forecast `horizon` rows (BASELINE metric); holdout: the reference "
+                         "contract -- hold out the last `horizon` rows, emit a fitted/forecast value for all T dates")
     ap.add_argument("--e2e-series", type=int, default=0, help="series per e2e step (0 = same as --series)")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl", "multicast", "multicast-bulk"],
                     help="N>1: how the forecast table reaches every rank: p2p = bulk stores from the fit kernel's epilogue "
@@ -223,7 +226,12 @@ def run_ours(args):
 
     eng = mmf.ForecastEngine(device=local, kernel=args.kernel)
     # ForecastEngine enqueues on torch's current stream for CUDA tensors, so the CUDA events below see the kernels
-    _, ps, npred = eng.plan_calendar(start, t, "D", h, "future")
+    _, ps, npred = eng.plan_calendar(start, t, "D", h, args.mode)
+    if args.mode == "holdout":
+        if world > 1:
+            raise SystemExit("--mode holdout is a single-GPU diagnostic")
+        table = torch.zeros((n, (npred + 3) & ~3), dtype=torch.float32, device=dev)[:, :npred]
+        mine = table
     st = eng.fit_forecast(y, ps, npred, out=mine, want_stats=True)["stats"]
     launches_per_call, kernel_used = st.kernel_launches, st.kernel_used
 
@@ -290,7 +298,7 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (algorithmic bytes: 4*T read + 4*H written per series)
     peak, peak_src = peaks()
-    bytes_per_series = 4 * t + 4 * h
+    bytes_per_series = 4 * t + 4 * h if args.mode == "future" else 4 * (t - h) + 4 * t
     achieved = n * bytes_per_series / (kern_ms_avg * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "kernel": "fit_tc_kernel" if kernel_used == "tc" else "fit_warp_kernel",
@@ -300,7 +308,7 @@ def run_ours(args):
 
     # ---- e2e: host (pinned) buffers through the C ABI, H2D + D2H inside the timed region
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and args.mode == "future":
         ne = args.e2e_series or n
         eng2 = mmf.ForecastEngine(device=local, kernel=args.kernel)
         eng2.plan_calendar(start, t, "D", h, "future")
@@ -337,7 +345,7 @@ def run_ours(args):
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"{n} (store,item) series x {t} days per GPU, {h}-day horizon, future mode "
                                        f"(BASELINE configs[3] shape; weak scaling)",
-                           "series_per_gpu": n, "t": t, "horizon": h, "nan_frac": args.nan_frac,
+                           "series_per_gpu": n, "t": t, "horizon": h, "nan_frac": args.nan_frac, "mode": args.mode,
                            "kernel": kernel_used, "l2": f"inputs {n * t * 4 / 1e9:.2f} GB per step per GPU > 126 MB L2",
                            "parallelism": f"series-sharded x{world}" + (f" + forecast table replicated to every rank via {gather}" if world > 1 else ""),
                            "gather": gather, "gather_max_abs_diff_vs_nccl": gather_check},

@@ -128,8 +128,9 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
     }
   } else if (warp >= WARP_EPI0 && warp < WARP_PROD) {
     // prediction rows of the whitened design -> shared (broadcast-read in the epilogue)
-    for (int i = threadIdx.x - WARP_EPI0 * 32; i < a.n_pred * P; i += 128)
-      s_apred[i] = __ldg(d.apred + (size_t)a.pred_start * P + i);
+    if (!a.skip_pred)
+      for (int i = threadIdx.x - WARP_EPI0 * 32; i < a.n_pred * P; i += 128)
+        s_apred[i] = __ldg(d.apred + (size_t)a.pred_start * P + i);
   }
   tc_fence_before();
   __syncthreads();
@@ -301,7 +302,7 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
     // Staged epilogue: the tile's forecasts are one contiguous block of the table (rows are dense), so they are
     // assembled in shared memory and leave as ONE bulk (TMA) store per destination -- full-size NVLink packets
     // for the peers' copies instead of 16-B stores scattered at a 112-B stride.
-    const bool bulk = vec_out && a.out_multimem != 1 && a.ld_out == a.n_pred && a.n_pred <= BULK_MAX_PRED;
+    const bool bulk = !a.skip_pred && vec_out && a.out_multimem != 1 && a.ld_out == a.n_pred && a.n_pred <= BULK_MAX_PRED;
     const uint32_t s_ostage_u32 = smem_u32(s_ostage);
     int lt = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
@@ -378,7 +379,7 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
             bulk_store_elect(reinterpret_cast<uint64_t>(a.out_more[i] + off), s_ostage_u32, bytes);
           bulk_commit_elect();
         }
-      } else if (live && !pend && !defer) {
+      } else if (live && !pend && !defer && !a.skip_pred) {
         const int64_t off = row * a.ld_out;
         if (vec_out) {
           for (int k = 0; k < a.n_pred; k += 4) {
@@ -393,6 +394,12 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
       }
       if (live) {
         if (!pend && !defer) {
+          if (a.out_gamma != nullptr) {
+            float4* gp = reinterpret_cast<float4*>(a.out_gamma + row * P);
+            gp[0] = make_float4(g[0], g[1], g[2], g[3]);    gp[1] = make_float4(g[4], g[5], g[6], g[7]);
+            gp[2] = make_float4(g[8], g[9], g[10], g[11]);  gp[3] = make_float4(g[12], g[13], g[14], g[15]);
+            a.out_c[row] = c;
+          }
           if (a.out_beta != nullptr) {
             float* __restrict__ br = a.out_beta + row * P;
             for (int p = 0; p < P; ++p) {
@@ -424,7 +431,7 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
 
 bool fit_tc_supported(const DesignView& d, const FitArgs& a, const char** why) {
   const char* w = nullptr;
-  if (a.n_pred > MAX_PRED) w = "n_pred > 64 (holdout/fitted mode uses the warp kernel)";
+  if (!a.skip_pred && a.n_pred > MAX_PRED) w = "n_pred > 64 needs the fit + predict_tc_kernel pair";
   else if (a.n_pred < 1) w = "n_pred < 1";
   else if (a.ld_y % 4 != 0) w = "ld_y not a multiple of 4 floats (TMA needs 16-B row pitch)";
   else if ((reinterpret_cast<uintptr_t>(a.y) & 15u) != 0) w = "y not 16-B aligned";

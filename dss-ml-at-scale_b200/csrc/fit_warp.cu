@@ -389,8 +389,20 @@ fit_warp_kernel(const DesignView d, const FitArgs a, const int smem_rows) {
 
     // ---- predictions for rows [pred_start, pred_start + n_pred): 4 series per design-row fetch
     const int64_t off0 = row0 * a.ld_out;
+    if (a.out_gamma != nullptr) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        if (act[s] && !deferred[s]) {
+          float gl = 0.f;
+#pragma unroll
+          for (int p = 0; p < P; ++p) gl = (lane == p) ? acc[s][p] : gl;
+          if (lane < P) a.out_gamma[(row0 + s) * P + lane] = any[s] ? gl : qnan;
+          if (lane == P) a.out_c[row0 + s] = any[s] ? c[s] : qnan;
+        }
+      }
+    }
 #pragma unroll 1
-    for (int k = lane; k < a.n_pred; k += 32) {
+    for (int k = lane; k < (a.skip_pred ? 0 : a.n_pred); k += 32) {
       const int t = a.pred_start + k;
       const float4 a0 = A.vec(0, t), a1 = A.vec(1, t), a2 = A.vec(2, t), a3 = A.vec(3, t);
 #pragma unroll

@@ -54,7 +54,7 @@ EncodeTiledFn get_encode_fn() {
 
 // 2-D fp32 tensor map: dims {inner, outer}, row pitch in bytes, box {box_inner, box_outer}, 128-B swizzle
 int encode_2d(void* out128, const void* gptr, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
-              uint32_t box_inner, uint32_t box_outer) {
+              uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(MMF_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {inner, outer};
@@ -63,7 +63,7 @@ int encode_2d(void* out128, const void* gptr, uint64_t inner, uint64_t outer, ui
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(reinterpret_cast<CUtensorMap*>(out128), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                   const_cast<void*>(gptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(MMF_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return MMF_OK;
 }
@@ -77,7 +77,11 @@ struct Plan {
   float* d_at = nullptr;
   float* d_apred = nullptr;
   float* d_w = nullptr;
+  float* d_ap_hi = nullptr;   // [n_rows][P] tf32-hi / tf32-lo of A: B operand of predict_tc_kernel
+  float* d_ap_lo = nullptr;
   alignas(64) unsigned char tmap_at[128];
+  alignas(64) unsigned char tmap_bhi[128];
+  alignas(64) unsigned char tmap_blo[128];
 };
 
 constexpr int NBUF = 3;
@@ -105,6 +109,10 @@ struct mmf_ctx {
   size_t recs_cap_bytes = 0;
   int64_t* d_rec_rows = nullptr;
   size_t rec_rows_cap_bytes = 0;
+  float* d_gamma = nullptr;            // [n][P] + d_c[n]: hand-off from the fit kernels to predict_tc_kernel
+  size_t gamma_cap_bytes = 0;
+  float* d_c = nullptr;
+  size_t c_cap_bytes = 0;
   int32_t* d_status_scratch = nullptr;
   size_t status_scratch_cap = 0;
   Plan plan;
@@ -114,7 +122,7 @@ struct mmf_ctx {
 namespace {
 
 void free_plan(Plan& p) {
-  cudaFree(p.d_a4); cudaFree(p.d_at); cudaFree(p.d_apred); cudaFree(p.d_w);
+  cudaFree(p.d_a4); cudaFree(p.d_at); cudaFree(p.d_apred); cudaFree(p.d_w); cudaFree(p.d_ap_hi); cudaFree(p.d_ap_lo);
   p = Plan{};
 }
 
@@ -156,6 +164,18 @@ int run_device(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, int32_t pr
   a.only_pending = 0; a.pending_count = nullptr;
   const char* why = nullptr;
   int kernel = ctx->cfg.kernel;
+  // Many prediction rows (the reference's "Demand_Fitted for every date", 02:484-494): fit kernels hand
+  // gamma/c to predict_tc_kernel, which writes the [n, n_pred] table with TMA stores.
+  const bool many_pred = n_pred > 64 && kernel != MMF_KERNEL_WARP && n_out == 1 && !multimem && ld_out % 4 == 0 &&
+                         (reinterpret_cast<uintptr_t>(out) & 15u) == 0 && n <= (int64_t)0x7fffffff - 128;
+  if (many_pred) {
+    int rc = grow((void**)&ctx->d_gamma, &ctx->gamma_cap_bytes, (size_t)n * P * sizeof(float));
+    if (rc == MMF_OK) rc = grow((void**)&ctx->d_c, &ctx->c_cap_bytes, (size_t)n * sizeof(float));
+    if (rc != MMF_OK) return rc;
+    a.out_gamma = ctx->d_gamma;
+    a.out_c = ctx->d_c;
+    a.skip_pred = 1;
+  }
   const bool tc_ok = fit_tc_supported(d, a, &why);
   if (kernel == MMF_KERNEL_TC && !tc_ok) return fail(MMF_E_UNSUPPORTED, "tcgen05 kernel not applicable: %s", why);
   if (kernel == MMF_KERNEL_AUTO) kernel = tc_ok ? MMF_KERNEL_TC : MMF_KERNEL_WARP;
@@ -195,6 +215,15 @@ int run_device(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, int32_t pr
       CU_TRY(launch_solve_rows(d, a, ctx->sm_count, s));
       ++*launches;
     }
+  }
+  if (many_pred) {
+    PredictLaunch pl;
+    memcpy(pl.tmap_bhi, ctx->plan.tmap_bhi, 128);
+    memcpy(pl.tmap_blo, ctx->plan.tmap_blo, 128);
+    int rc = encode_2d(pl.tmap_out, out, (uint64_t)n_pred, (uint64_t)n, (uint64_t)ld_out * 4, 32, 128);
+    if (rc != MMF_OK) return rc;
+    CU_TRY(launch_predict_tc(d, a, pl, ctx->sm_count, s));
+    ++*launches;
   }
   *kernel_used = kernel;
   return MMF_OK;
@@ -284,6 +313,8 @@ int mmf_destroy(mmf_ctx* ctx) {
   cudaFree(ctx->d_pending);
   cudaFree(ctx->d_recs);
   cudaFree(ctx->d_rec_rows);
+  cudaFree(ctx->d_gamma);
+  cudaFree(ctx->d_c);
   cudaFree(ctx->d_status_scratch);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
@@ -398,6 +429,15 @@ int mmf_plan_design(mmf_ctx* ctx, const double* X, int32_t n_rows, int32_t p, in
     }
   float w32[P * P];
   for (int i = 0; i < P * P; ++i) w32[i] = (float)pl.W[i];
+  std::vector<float> ap_hi(A.size()), ap_lo(A.size());
+  for (size_t i = 0; i < A.size(); ++i) {
+    const float v = A[i];
+    uint32_t hb; memcpy(&hb, &v, 4); hb &= 0xFFFFE000u;
+    float hi; memcpy(&hi, &hb, 4);
+    float lo = v - hi;
+    uint32_t lb; memcpy(&lb, &lo, 4); lb &= 0xFFFFE000u; memcpy(&lo, &lb, 4);
+    ap_hi[i] = hi; ap_lo[i] = lo;
+  }
 
   CU_TRY(cudaMalloc(&pl.d_a4, a4.size() * sizeof(float)));
   CU_TRY(cudaMalloc(&pl.d_at, at.size() * sizeof(float)));
@@ -407,7 +447,15 @@ int mmf_plan_design(mmf_ctx* ctx, const double* X, int32_t n_rows, int32_t p, in
   CU_TRY(cudaMemcpy(pl.d_at, at.data(), at.size() * sizeof(float), cudaMemcpyHostToDevice));
   CU_TRY(cudaMemcpy(pl.d_apred, A.data(), A.size() * sizeof(float), cudaMemcpyHostToDevice));
   CU_TRY(cudaMemcpy(pl.d_w, w32, sizeof(w32), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMalloc(&pl.d_ap_hi, A.size() * sizeof(float)));
+  CU_TRY(cudaMalloc(&pl.d_ap_lo, A.size() * sizeof(float)));
+  CU_TRY(cudaMemcpy(pl.d_ap_hi, ap_hi.data(), A.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(pl.d_ap_lo, ap_lo.data(), A.size() * sizeof(float), cudaMemcpyHostToDevice));
   int rc = encode_2d(pl.tmap_at, pl.d_at, (uint64_t)pl.t_pad, (uint64_t)(2 * P), (uint64_t)pl.t_pad * 4, 32, 2 * P);
+  if (rc != MMF_OK) return rc;
+  rc = encode_2d(pl.tmap_bhi, pl.d_ap_hi, (uint64_t)P, (uint64_t)n_rows, (uint64_t)P * 4, P, 128, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (rc != MMF_OK) return rc;
+  rc = encode_2d(pl.tmap_blo, pl.d_ap_lo, (uint64_t)P, (uint64_t)n_rows, (uint64_t)P * 4, P, 128, CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc != MMF_OK) return rc;
   pl.valid = true;
   return MMF_OK;

@@ -55,6 +55,9 @@ struct FitArgs {
   float* out_more[MAX_OUT - 1];   // peer-mapped copies of the table slice (NVLink P2P stores), n_out - 1 valid
   int32_t n_out;            // 1 = local only
   int32_t out_multimem;     // `out` is an NVLS multicast address: 1 -> multimem.st per row, 2 -> bulk (TMA) stores to it
+  float* out_gamma;         // nullable [n][P]: whitened coefficients (+ out_c[n]) for predict_tc_kernel
+  float* out_c;
+  int32_t skip_pred;        // 1: fit only (gamma/c out); predictions come from predict_tc_kernel
   float* out_beta;          // nullable [n][P]
   int32_t* status;          // never null inside the library (scratch if caller passed NULL)
   SolveRec* recs;           // nullable: [n] records by row; series with gaps are deferred to solve_rows_kernel
@@ -72,6 +75,16 @@ size_t fit_warp_smem_bytes(const DesignView& d, int* smem_rows);
 // thread-per-series normal equations for the deferred masked rows: Gram downdate, in-order Cholesky with
 // pivot dropping and both triangular solves entirely in registers, then the forecasts
 cudaError_t launch_solve_rows(const DesignView& d, const FitArgs& a, int sm_count, cudaStream_t s);
+
+// fitted values + forecasts for MANY prediction rows (the reference's "Demand_Fitted for every date"
+// contract, 02:484-494): out[n, n_pred] = c + gamma A_pred^T as a tcgen05 GEMM with TMA-stored tiles
+struct PredictLaunch {
+  alignas(64) unsigned char tmap_bhi[128];
+  alignas(64) unsigned char tmap_blo[128];
+  alignas(64) unsigned char tmap_out[128];
+};
+cudaError_t launch_predict_tc(const DesignView& d, const FitArgs& a, const PredictLaunch& pl, int sm_count,
+                              cudaStream_t s);
 
 // TMA + tcgen05/TMEM kernel (fully observed fast path).  `tmap_y` / `tmap_at` are CUtensorMap blobs.
 struct TcLaunch {

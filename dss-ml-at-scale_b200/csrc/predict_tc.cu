@@ -1,0 +1,239 @@
+// predict_tc.cu -- fitted values + forecasts for every requested date: out[n, n_pred] = c + gamma A_pred^T.
+//
+// The reference's per-group UDF returns Demand_Fitted for EVERY date of the group (in-sample fits for the train
+// dates + the forecast for the held-out dates, group_apply/02_Fine_Grained_Demand_Forecasting.py:484-494).  With
+// T dates per series that is as many bytes out as the fit read in, and 16 FMAs per output element -- too much for
+// the CUDA cores at HBM speed, so it is a second tcgen05 GEMM, the mirror image of fit_tc.cu:
+//   A operand  gamma tile [128 series x 16] (fp32 split hi/lo, written once per tile with tcgen05.st)  -> TMEM
+//   B operand  prediction rows of the whitened design, [128 t x 16] K-major tiles (hi and lo), TMA, 64-B swizzle
+//   D          [128 series x 128 t] fp32 in TMEM, double buffered:  hi*Bhi + hi*Blo + lo*Bhi  (fp32-grade)
+//   epilogue   tcgen05.ld -> + c -> 128-B-swizzled shared tiles -> TMA 2-D stores (clipped at n / n_pred)
+// Bound: HBM writes, 4*n_pred bytes per series.
+#include "mmf_internal.cuh"
+#include "sm100_ptx.cuh"
+
+namespace mmf {
+namespace {
+
+using namespace sm100;
+
+constexpr int TILE_M = 128;                   // series per tile == TMEM lanes
+constexpr int TN = 128;                       // prediction rows per chunk == D columns
+constexpr int SB = 3;                         // B-operand stages
+constexpr int B_TILE_BYTES = TN * P * 4;      // 8192 (hi) ; same for lo
+constexpr int B_STAGE_BYTES = 2 * B_TILE_BYTES;
+constexpr int OUT_SUB_BYTES = TILE_M * 32 * 4;          // one {32 t x 128 series} store box: 16384
+constexpr int OUT_STAGE_BYTES = (TN / 32) * OUT_SUB_BYTES;   // 65536
+constexpr int THREADS = 320;
+constexpr int WARP_LOAD0 = 4, WARP_PROD = 8, WARP_MMA = 9;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t D_COL0 = 0;                // 2 x 128 accumulator columns
+constexpr uint32_t A_COL0 = 256;              // 2 x (16 hi + 16 lo)
+
+struct Smem {
+  static constexpr int b = 0;
+  static constexpr int out = b + SB * B_STAGE_BYTES;                // 24576
+  static constexpr int bars = out + 2 * OUT_STAGE_BYTES;            // + 131072
+  static constexpr int n_bars = 2 * SB + 4 + 4;
+  static constexpr int tmem_ptr = bars + n_bars * 8;
+  static constexpr int total = tmem_ptr + 16;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+predict_tc_kernel(const __grid_constant__ PredictLaunch pl, const DesignView d, const FitArgs a, const int n_tiles,
+                  const int n_chunks) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t s_b = sbase + Smem::b;
+  const uint32_t s_out = sbase + Smem::out;
+  const uint32_t s_bars = sbase + Smem::bars;
+  auto bar_bfull = [&](int s) { return s_bars + 8u * s; };
+  auto bar_bempty = [&](int s) { return s_bars + 8u * (SB + s); };
+  auto bar_afull = [&](int i) { return s_bars + 8u * (2 * SB + i); };
+  auto bar_aempty = [&](int i) { return s_bars + 8u * (2 * SB + 2 + i); };
+  auto bar_dfull = [&](int i) { return s_bars + 8u * (2 * SB + 4 + i); };
+  auto bar_dempty = [&](int i) { return s_bars + 8u * (2 * SB + 6 + i); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + Smem::tmem_ptr);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == WARP_MMA) {
+    if (lane == 0) {
+      for (int s = 0; s < SB; ++s) { mbar_init(bar_bfull(s), 1); mbar_init(bar_bempty(s), 1); }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(bar_afull(i), 4);    // 4 loader warps
+        mbar_init(bar_aempty(i), 1);   // tcgen05.commit after the tile's last chunk
+        mbar_init(bar_dfull(i), 1);    // tcgen05.commit per chunk
+        mbar_init(bar_dempty(i), 4);   // 4 epilogue warps
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), TMEM_COLS);
+    tmem_relinquish();
+  } else if (warp == WARP_PROD && lane == 0) {
+    prefetch_tensormap(pl.tmap_bhi);
+    prefetch_tensormap(pl.tmap_blo);
+    prefetch_tensormap(pl.tmap_out);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == WARP_PROD) {
+    // =========================== TMA producer: design rows of the prediction window ===========================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        mbar_wait(bar_bempty(stage), phase ^ 1u);
+        const int t0 = a.pred_start + ch * TN;
+        tma_load_2d_x2_elect(bar_bfull(stage), B_STAGE_BYTES,
+                             s_b + stage * B_STAGE_BYTES, pl.tmap_bhi, 0, t0, L2_EVICT_LAST,
+                             s_b + stage * B_STAGE_BYTES + B_TILE_BYTES, pl.tmap_blo, 0, t0, L2_EVICT_LAST);
+        if (++stage == SB) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == WARP_MMA) {
+    // =========================== MMA issuer ===========================
+    constexpr uint32_t IDESC = umma_idesc_tf32(TILE_M, TN);
+    int stage = 0, db = 0, lt = 0;
+    uint32_t phase = 0, dphase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+      const int ab = lt & 1;
+      mbar_wait(bar_afull(ab), (lt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t a_hi = tmem_base + A_COL0 + ab * 32;
+      const uint32_t a_lo = a_hi + 16;
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        mbar_wait(bar_bfull(stage), phase);
+        mbar_wait(bar_dempty(db), dphase ^ 1u);
+        tc_fence_after();
+        const uint64_t bhi = umma_desc_k_sw64(s_b + stage * B_STAGE_BYTES);
+        const uint64_t blo = umma_desc_k_sw64(s_b + stage * B_STAGE_BYTES + B_TILE_BYTES);
+        const uint32_t dcol = tmem_base + D_COL0 + db * TN;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          umma_tf32_ts_elect(dcol, a_hi + k * 8, bhi + static_cast<uint64_t>(k * 2), IDESC, k ? 1u : 0u);
+          umma_tf32_ts_elect(dcol, a_hi + k * 8, blo + static_cast<uint64_t>(k * 2), IDESC, 1u);
+          umma_tf32_ts_elect(dcol, a_lo + k * 8, bhi + static_cast<uint64_t>(k * 2), IDESC, 1u);
+        }
+        umma_commit_elect(bar_bempty(stage));
+        umma_commit_elect(bar_dfull(db));
+        if (ch == n_chunks - 1) umma_commit_elect(bar_aempty(ab));
+        if (++stage == SB) { stage = 0; phase ^= 1u; }
+        if (++db == 2) { db = 0; dphase ^= 1u; }
+      }
+    }
+  } else if (warp >= WARP_LOAD0) {
+    // =========================== gamma loaders (warps 4-7): one tcgen05.st pair per tile ===========================
+    const int r = threadIdx.x & 127;
+    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+      const int ab = lt & 1;
+      const int64_t row = (int64_t)tile * TILE_M + r;
+      float g[P];
+      if (row < a.n) {
+        const float4* gp = reinterpret_cast<const float4*>(a.out_gamma + row * P);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 v = __ldg(gp + q);
+          g[4 * q] = v.x; g[4 * q + 1] = v.y; g[4 * q + 2] = v.z; g[4 * q + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int p = 0; p < P; ++p) g[p] = 0.f;
+      }
+      uint32_t hi[P], lo[P];
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        const uint32_t h = __float_as_uint(g[p]) & 0xFFFFE000u;
+        hi[p] = h;
+        lo[p] = __float_as_uint(g[p] - __uint_as_float(h));
+      }
+      mbar_wait(bar_aempty(ab), ((lt >> 1) & 1) ^ 1u);
+      tc_fence_after();
+      const uint32_t acol = tmem_base + lane_addr + A_COL0 + ab * 32;
+      tmem_st_32x32b_x16(acol, hi);
+      tmem_st_32x32b_x16(acol + 16, lo);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_afull(ab));
+    }
+  } else {
+    // =========================== epilogue (warps 0-3): D -> + c -> swizzled tiles -> TMA store ===========================
+    const int r = threadIdx.x;
+    const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t row_off = static_cast<uint32_t>(r) * 128u;
+    const uint32_t sw = static_cast<uint32_t>(r & 7);
+    int db = 0, ob = 0;
+    uint32_t dphase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t row = (int64_t)tile * TILE_M + r;
+      const float c = (row < a.n) ? __ldg(a.out_c + row) : 0.f;
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        mbar_wait(bar_dfull(db), dphase);
+        tc_fence_after();
+        // the staging buffer `ob` was handed to TMA two chunks ago: its reads must be done before we overwrite it
+        if (warp == 0) bulk_wait_read1_elect();
+        named_bar_sync(1, 128);
+        const uint32_t obase = s_out + ob * OUT_STAGE_BYTES;
+#pragma unroll
+        for (int j = 0; j < TN / 32; ++j) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + lane_addr + D_COL0 + db * TN + j * 32, v);
+          tmem_wait_ld();
+          const uint32_t rowp = obase + j * OUT_SUB_BYTES + row_off;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 o = make_float4(__uint_as_float(v[4 * q]) + c, __uint_as_float(v[4 * q + 1]) + c,
+                                         __uint_as_float(v[4 * q + 2]) + c, __uint_as_float(v[4 * q + 3]) + c);
+            sts128(rowp + ((static_cast<uint32_t>(q) ^ sw) << 4), o);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_dempty(db));       // accumulator buffer free for the MMA warp
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (warp == 0) {
+#pragma unroll
+          for (int j = 0; j < TN / 32; ++j)
+            tma_store_2d_elect(pl.tmap_out, obase + j * OUT_SUB_BYTES, ch * TN + j * 32, tile * TILE_M);
+          bulk_commit_elect();
+        }
+        ob ^= 1;
+        if (++db == 2) { db = 0; dphase ^= 1u; }
+      }
+    }
+    if (warp == 0) bulk_wait_all_elect();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WARP_MMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_predict_tc(const DesignView& d, const FitArgs& a, const PredictLaunch& pl, int sm_count,
+                              cudaStream_t s) {
+  if (a.n <= 0) return cudaSuccess;
+  const int n_tiles = (int)((a.n + TILE_M - 1) / TILE_M);
+  const int n_chunks = (a.n_pred + TN - 1) / TN;
+  const size_t smem = Smem::total + 1024;
+  cudaError_t e = cudaFuncSetAttribute(predict_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int grid = n_tiles < sm_count ? n_tiles : sm_count;
+  predict_tc_kernel<<<grid, THREADS, smem, s>>>(pl, d, a, n_tiles, n_chunks);
+  return cudaGetLastError();
+}
+
+}  // namespace mmf

@@ -123,6 +123,12 @@ __device__ __forceinline__ void bulk_wait_read_elect() {       // the elected la
       "elect.sync _|pe, 0xffffffff;\n\t"
       "@pe cp.async.bulk.wait_group.read 0;\n\t}" ::: "memory");
 }
+__device__ __forceinline__ void bulk_wait_read1_elect() {      // all but the most recent bulk group have read smem
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe cp.async.bulk.wait_group.read 1;\n\t}" ::: "memory");
+}
 __device__ __forceinline__ void bulk_wait_all_elect() {        // ... and have been written to global
   asm volatile(
       "{\n\t.reg .pred pe;\n\t"
@@ -172,6 +178,37 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
         "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
         "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
+}
+
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+// 2-D tiled store shared -> global through a tensor map (clips at the tensor bounds); warp-converged, elected lane
+__device__ __forceinline__ void tma_store_2d_elect(const void* tmap, uint32_t src_smem, int32_t c0, int32_t c1) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n\t}"
+      ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src_smem), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// Shared-memory matrix descriptor, K-major, SWIZZLE_64B, 32-bit elements: rows are 64 B (16 elements),
+// 8-row groups 512 B apart (SBO), tile base 512-B aligned.
+__device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;                            // SWIZZLE_64B
+  return d;
 }
 
 // ---- UMMA descriptors --------------------------------------------------------
@@ -252,6 +289,9 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
                : "memory");
 }
 
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));

@@ -94,10 +94,16 @@ solve_rows_kernel(const DesignView d, const FitArgs a) {
       b[j] = ((outmask >> j) & 1u) ? 0.f : s / G[tri(j, j)];
     }
 
+    if (a.out_gamma != nullptr) {
+      float4* gp = reinterpret_cast<float4*>(a.out_gamma + row * P);
+      gp[0] = make_float4(b[0], b[1], b[2], b[3]);    gp[1] = make_float4(b[4], b[5], b[6], b[7]);
+      gp[2] = make_float4(b[8], b[9], b[10], b[11]);  gp[3] = make_float4(b[12], b[13], b[14], b[15]);
+      a.out_c[row] = c;
+    }
     // ---- forecasts
     const int64_t off = row * a.ld_out;
 #pragma unroll 1
-    for (int k = 0; k < a.n_pred; ++k) {
+    for (int k = 0; k < (a.skip_pred ? 0 : a.n_pred); ++k) {
       const float4* ap = reinterpret_cast<const float4*>(d.apred + (size_t)(a.pred_start + k) * P);
       const float4 a0 = __ldg(ap), a1 = __ldg(ap + 1), a2 = __ldg(ap + 2), a3 = __ldg(ap + 3);
       float s = c;

@@ -185,8 +185,10 @@ class ForecastEngine:
         def make(shape, np_dtype):
             if on_dev:
                 import torch
-                return torch.empty(shape, device=y.device,
-                                   dtype=torch.float32 if np_dtype == np.float32 else torch.int32)
+                dt = torch.float32 if np_dtype == np.float32 else torch.int32
+                if len(shape) == 2 and shape[1] % 4:          # 16-B row pitch: TMA-storable by predict_tc_kernel
+                    return torch.empty((shape[0], (shape[1] + 3) & ~3), device=y.device, dtype=dt)[:, :shape[1]]
+                return torch.empty(shape, device=y.device, dtype=dt)
             return np.empty(shape, dtype=np_dtype)
 
         if out is None:

@@ -296,3 +296,24 @@ def test_broadcast_stores_write_every_replica(engines):
         torch.cuda.synchronize()
         for r in reps:
             assert torch.equal(r, want), k
+
+
+@pytest.mark.parametrize("n,t", [(300, 1095), (1000, 400), (129, 157), (5, 130)])
+def test_holdout_on_tensor_cores_matches_oracle_and_warp(engines, n, t):
+    """Reference contract (02:484-494): a value for EVERY grid date.  auto/tc = fit kernels + predict_tc_kernel
+    (tcgen05 GEMM + TMA stores), warp = CUDA-core path; both against the float64 oracle, incl. rows with gaps."""
+    y, start = mmf.synth.daily_store_item_demand(n, t, seed=300 + n)
+    y[1, 10:40] = np.nan
+    y[2, :] = np.nan                                  # empty row -> NaN everywhere, status 1
+    y[3, 0] = np.nan
+    want, wst = _oracle(y, start, "D", 28, "holdout")
+    outs = {}
+    for k in ("auto", "tc", "warp"):
+        pred, status, res = _run(engines[k], y, start, "D", 28, "holdout", want_stats=True)
+        assert np.array_equal(status, wst), k
+        ok = wst != 1
+        assert np.isnan(pred[~ok]).all()
+        assert np.abs(pred[ok] - want[ok]).max() <= tolerance(y), k
+        outs[k] = pred
+        assert res["stats"].kernel_used == ("warp" if k == "warp" else "tc")
+    assert np.nanmax(np.abs(outs["auto"] - outs["warp"])) <= tolerance(y)
