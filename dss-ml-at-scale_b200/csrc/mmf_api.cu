@@ -629,6 +629,51 @@ int mmf_fit_forecast_bcast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t 
                     status, ctx->stream, &launches, &kernel_used, more, n_out, multimem);
 }
 
+// ---- device-side packer (pack.cu): every pointer is a device pointer, work is enqueued on the ctx stream
+#define PACK_PROLOGUE()                                              \
+  if (!ctx) return fail(MMF_E_INVALID, "ctx is NULL");               \
+  if (n < 0) return fail(MMF_E_INVALID, "n < 0");                    \
+  CU_TRY(cudaSetDevice(ctx->device));
+
+int mmf_pack_hash_utf8(mmf_ctx* ctx, const int32_t* offsets, const uint8_t* data, int64_t n, uint64_t* hash,
+                       int32_t first) {
+  PACK_PROLOGUE();
+  CU_TRY(pack_hash_utf8(offsets, data, n, hash, first, ctx->sm_count, ctx->stream));
+  return MMF_OK;
+}
+
+int mmf_pack_hash_i32(mmf_ctx* ctx, const int32_t* values, int64_t n, uint64_t* hash, int32_t first) {
+  PACK_PROLOGUE();
+  CU_TRY(pack_hash_i32(values, n, hash, first, ctx->sm_count, ctx->stream));
+  return MMF_OK;
+}
+
+int mmf_pack_group_codes(mmf_ctx* ctx, const uint64_t* hash, int64_t n, int32_t* gid, int32_t* first_row,
+                         int32_t* n_groups) {
+  PACK_PROLOGUE();
+  if (!n_groups) return fail(MMF_E_INVALID, "n_groups is NULL");
+  if (n > 0x7fffffff) return fail(MMF_E_UNSUPPORTED, "more than 2^31-1 rows in one pack call");
+  CU_TRY(pack_group_codes(hash, n, gid, first_row, n_groups, ctx->sm_count, ctx->stream));
+  return MMF_OK;
+}
+
+int mmf_pack_minmax(mmf_ctx* ctx, const int32_t* gid, const int32_t* day, int64_t n, int32_t n_groups,
+                    int32_t* gmin, int32_t* gmax) {
+  PACK_PROLOGUE();
+  CU_TRY(pack_minmax(gid, day, n, n_groups, gmin, gmax, ctx->sm_count, ctx->stream));
+  return MMF_OK;
+}
+
+int mmf_pack_scatter_f32(mmf_ctx* ctx, const int32_t* gid, const int32_t* day, const float* val, int64_t n,
+                         const int64_t* row_of_group, const int32_t* gstart, int32_t step, float* y, int64_t n_rows,
+                         int64_t ld_y, int32_t t_len) {
+  PACK_PROLOGUE();
+  if (step < 1 || ld_y % 4 != 0 || ld_y < t_len || (reinterpret_cast<uintptr_t>(y) & 15u) != 0)
+    return fail(MMF_E_INVALID, "need step >= 1, a 16-B aligned y and ld_y >= t_len, ld_y %% 4 == 0");
+  CU_TRY(pack_scatter(gid, day, val, n, row_of_group, gstart, step, y, n_rows, ld_y, t_len, ctx->sm_count, ctx->stream));
+  return MMF_OK;
+}
+
 int mmf_alloc_pinned(size_t bytes, void** out) {
   if (!out) return fail(MMF_E_INVALID, "out is NULL");
   CU_TRY(cudaHostAlloc(out, bytes, cudaHostAllocDefault));

@@ -95,6 +95,18 @@ cudaError_t launch_fit_tc(const DesignView& d, const FitArgs& a, const TcLaunch&
                           uint32_t* pending_count, int sm_count, cudaStream_t s);
 bool fit_tc_supported(const DesignView& d, const FitArgs& a, const char** why);
 
+// device-side packer (pack.cu)
+cudaError_t pack_hash_utf8(const int32_t* offsets, const uint8_t* data, int64_t n, uint64_t* h, int first, int sm,
+                           cudaStream_t s);
+cudaError_t pack_hash_i32(const int32_t* v, int64_t n, uint64_t* h, int first, int sm, cudaStream_t s);
+cudaError_t pack_group_codes(const uint64_t* h, int64_t n, int32_t* gid, int32_t* first_row, int32_t* n_groups_host,
+                             int sm, cudaStream_t s);
+cudaError_t pack_minmax(const int32_t* gid, const int32_t* day, int64_t n, int32_t n_groups, int32_t* gmin,
+                        int32_t* gmax, int sm, cudaStream_t s);
+cudaError_t pack_scatter(const int32_t* gid, const int32_t* day, const float* val, int64_t n,
+                         const int64_t* row_of_group, const int32_t* gstart, int32_t step, float* y, int64_t n_rows,
+                         int64_t ld_y, int32_t t_len, int sm, cudaStream_t s);
+
 #ifdef __CUDACC__
 // Forecast stores: plain, NVSwitch multicast (multimem.st) or fan-out over peer-mapped pointers.
 __device__ __forceinline__ void store_out1(const FitArgs& a, int64_t off, float v) {

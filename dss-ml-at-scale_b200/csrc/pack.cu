@@ -1,0 +1,181 @@
+// pack.cu -- device-side packer: long-format (key, Date, Demand) rows -> padded series y[N, T] on the GPU.
+//
+// Replaces, for all groups at once, what Spark + pandas do before the per-group fit in the reference:
+// the hash shuffle of `repartition(n_tasks, "Product", "SKU")` + `groupBy` (02:525-526) and the per-group
+// `sort_values("Date")` + `set_index("Date").asfreq(freq)` (02:422-423).  Inputs are Arrow column buffers
+// copied to the device as they are (utf8 offsets + bytes or dictionary indices for the keys, date32 days,
+// float32 values); nothing is sorted by the caller.
+//   1. hash_utf8 / hash_i32      64-bit FNV-1a of each row's key columns (chained across columns)
+//   2. group codes               cub radix sort of (hash,row) -> segment heads -> dense codes 0..G-1,
+//                                first row of every group (to recover its key strings on the host)
+//   3. minmax                    per-group first / last day (warp-aggregated atomics)
+//   4. scatter                   y[row_of_group[g], (day - start_g) / step] = value   (NaN-prefilled)
+// Every step is HBM-bound integer / byte work: coalesced streaming reads, one scattered 4-B write per row.
+#include <cub/cub.cuh>
+
+#include "mmf_internal.cuh"
+
+namespace mmf {
+namespace {
+
+constexpr int TPB = 256;
+
+__device__ __forceinline__ uint64_t fnv1a_byte(uint64_t h, uint32_t b) { return (h ^ b) * 1099511628211ull; }
+
+__global__ void hash_utf8_kernel(const int32_t* __restrict__ offsets, const uint8_t* __restrict__ data, int64_t n,
+                                 uint64_t* __restrict__ h, int first) {
+  for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += (int64_t)gridDim.x * TPB) {
+    uint64_t x = first ? 14695981039346656037ull : h[i];
+    const int32_t lo = offsets[i], hi = offsets[i + 1];
+    for (int32_t k = lo; k < hi; ++k) x = fnv1a_byte(x, data[k]);
+    x = fnv1a_byte(x, 0xffu);                       // column separator: ("ab","c") != ("a","bc")
+    h[i] = x;
+  }
+}
+
+__global__ void hash_i32_kernel(const int32_t* __restrict__ v, int64_t n, uint64_t* __restrict__ h, int first) {
+  for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += (int64_t)gridDim.x * TPB) {
+    uint64_t x = first ? 14695981039346656037ull : h[i];
+    const uint32_t u = static_cast<uint32_t>(v[i]);
+    x = fnv1a_byte(x, u & 0xffu); x = fnv1a_byte(x, (u >> 8) & 0xffu);
+    x = fnv1a_byte(x, (u >> 16) & 0xffu); x = fnv1a_byte(x, u >> 24);
+    x = fnv1a_byte(x, 0xffu);
+    h[i] = x;
+  }
+}
+
+__global__ void iota_kernel(int32_t* __restrict__ v, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += (int64_t)gridDim.x * TPB) v[i] = (int32_t)i;
+}
+
+__global__ void heads_kernel(const uint64_t* __restrict__ sorted_h, int64_t n, int32_t* __restrict__ head) {
+  for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += (int64_t)gridDim.x * TPB)
+    head[i] = (i == 0 || sorted_h[i] != sorted_h[i - 1]) ? 1 : 0;
+}
+
+// code of sorted position i = (inclusive scan of heads)[i] - 1 ; scatter back to the original row order
+__global__ void codes_kernel(const int32_t* __restrict__ scan, const int32_t* __restrict__ head,
+                             const int32_t* __restrict__ sorted_row, int64_t n, int32_t* __restrict__ gid,
+                             int32_t* __restrict__ first_row) {
+  for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += (int64_t)gridDim.x * TPB) {
+    const int32_t g = scan[i] - 1;
+    gid[sorted_row[i]] = g;
+    if (head[i]) first_row[g] = sorted_row[i];
+  }
+}
+
+__global__ void minmax_kernel(const int32_t* __restrict__ gid, const int32_t* __restrict__ day, int64_t n,
+                              int32_t* __restrict__ gmin, int32_t* __restrict__ gmax) {
+  const int64_t stride = (int64_t)gridDim.x * TPB;
+  for (int64_t i0 = (int64_t)blockIdx.x * TPB; i0 < n; i0 += stride) {
+    const int64_t i = i0 + threadIdx.x;
+    const bool live = i < n;
+    const int32_t g = live ? gid[i] : -1;
+    const int32_t d = live ? day[i] : 0;
+    // rows of one group are usually adjacent: one atomic per (warp, group) instead of one per row
+    const unsigned peers = __match_any_sync(0xffffffffu, g);
+    const int32_t lo = __reduce_min_sync(peers, d);
+    const int32_t hi = __reduce_max_sync(peers, d);
+    if (live && (threadIdx.x & 31) == (__ffs(peers) - 1)) {
+      atomicMin(gmin + g, lo);
+      atomicMax(gmax + g, hi);
+    }
+  }
+}
+
+__global__ void fill_nan_kernel(float4* __restrict__ y, int64_t n4) {
+  const float qn = __int_as_float(0x7fc00000);
+  const float4 v = make_float4(qn, qn, qn, qn);
+  for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n4; i += (int64_t)gridDim.x * TPB) __stcs(y + i, v);
+}
+
+__global__ void scatter_kernel(const int32_t* __restrict__ gid, const int32_t* __restrict__ day,
+                               const float* __restrict__ val, int64_t n, const int64_t* __restrict__ row_of_group,
+                               const int32_t* __restrict__ gstart, int32_t step, float* __restrict__ y, int64_t ld_y,
+                               int32_t t_len) {
+  for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += (int64_t)gridDim.x * TPB) {
+    const int32_t g = gid[i];
+    const int64_t r = row_of_group[g];
+    if (r < 0) continue;                            // group belongs to another calendar bucket
+    const int32_t off = day[i] - gstart[g];
+    if (off < 0 || off % step != 0) continue;       // off-grid rows vanish, like asfreq (02:423)
+    const int32_t t = off / step;
+    if (t < t_len) y[r * ld_y + t] = val[i];
+  }
+}
+
+unsigned grid_for(int64_t n, int sm_count) {
+  const int64_t want = (n + TPB - 1) / TPB;
+  const int64_t cap = (int64_t)sm_count * 16;
+  return (unsigned)std::max<int64_t>(1, std::min(want, cap));
+}
+
+}  // namespace
+
+cudaError_t pack_hash_utf8(const int32_t* offsets, const uint8_t* data, int64_t n, uint64_t* h, int first, int sm,
+                           cudaStream_t s) {
+  if (n > 0) hash_utf8_kernel<<<grid_for(n, sm), TPB, 0, s>>>(offsets, data, n, h, first);
+  return cudaGetLastError();
+}
+cudaError_t pack_hash_i32(const int32_t* v, int64_t n, uint64_t* h, int first, int sm, cudaStream_t s) {
+  if (n > 0) hash_i32_kernel<<<grid_for(n, sm), TPB, 0, s>>>(v, n, h, first);
+  return cudaGetLastError();
+}
+
+// hash[n] -> gid[n] (dense codes in hash order), first_row[>= n_groups], *n_groups.  Synchronises once (to read G).
+cudaError_t pack_group_codes(const uint64_t* h, int64_t n, int32_t* gid, int32_t* first_row, int32_t* n_groups_host,
+                             int sm, cudaStream_t s) {
+  *n_groups_host = 0;
+  if (n <= 0) return cudaSuccess;
+  uint64_t* h_sorted = nullptr;
+  int32_t *rows = nullptr, *rows_sorted = nullptr, *head = nullptr, *scan = nullptr;
+  void* tmp = nullptr;
+  size_t tmp_sort = 0, tmp_scan = 0;
+  cudaError_t e;
+  auto cleanup = [&]() {
+    cudaFree(h_sorted); cudaFree(rows); cudaFree(rows_sorted); cudaFree(head); cudaFree(scan); cudaFree(tmp);
+  };
+#define PK_TRY(x) do { e = (x); if (e != cudaSuccess) { cleanup(); return e; } } while (0)
+  PK_TRY(cudaMalloc(&h_sorted, n * sizeof(uint64_t)));
+  PK_TRY(cudaMalloc(&rows, n * sizeof(int32_t)));
+  PK_TRY(cudaMalloc(&rows_sorted, n * sizeof(int32_t)));
+  PK_TRY(cudaMalloc(&head, n * sizeof(int32_t)));
+  PK_TRY(cudaMalloc(&scan, n * sizeof(int32_t)));
+  PK_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, h, h_sorted, rows, rows_sorted, (int)n, 0, 64, s));
+  PK_TRY(cub::DeviceScan::InclusiveSum(nullptr, tmp_scan, head, scan, (int)n, s));
+  PK_TRY(cudaMalloc(&tmp, std::max(tmp_sort, tmp_scan)));
+  iota_kernel<<<grid_for(n, sm), TPB, 0, s>>>(rows, n);
+  size_t t1 = tmp_sort;
+  PK_TRY(cub::DeviceRadixSort::SortPairs(tmp, t1, h, h_sorted, rows, rows_sorted, (int)n, 0, 64, s));
+  heads_kernel<<<grid_for(n, sm), TPB, 0, s>>>(h_sorted, n, head);
+  size_t t2 = tmp_scan;
+  PK_TRY(cub::DeviceScan::InclusiveSum(tmp, t2, head, scan, (int)n, s));
+  codes_kernel<<<grid_for(n, sm), TPB, 0, s>>>(scan, head, rows_sorted, n, gid, first_row);
+  PK_TRY(cudaGetLastError());
+  PK_TRY(cudaMemcpyAsync(n_groups_host, scan + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  PK_TRY(cudaStreamSynchronize(s));
+#undef PK_TRY
+  cleanup();
+  return cudaSuccess;
+}
+
+cudaError_t pack_minmax(const int32_t* gid, const int32_t* day, int64_t n, int32_t n_groups, int32_t* gmin,
+                        int32_t* gmax, int sm, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(gmin, 0x7f, (size_t)n_groups * sizeof(int32_t), s);     // 0x7f7f7f7f: > any date32
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(gmax, 0x80, (size_t)n_groups * sizeof(int32_t), s);                 // 0x80808080: < any date32
+  if (e != cudaSuccess) return e;
+  if (n > 0) minmax_kernel<<<grid_for(n, sm), TPB, 0, s>>>(gid, day, n, gmin, gmax);
+  return cudaGetLastError();
+}
+
+cudaError_t pack_scatter(const int32_t* gid, const int32_t* day, const float* val, int64_t n,
+                         const int64_t* row_of_group, const int32_t* gstart, int32_t step, float* y, int64_t n_rows,
+                         int64_t ld_y, int32_t t_len, int sm, cudaStream_t s) {
+  const int64_t n4 = n_rows * ld_y / 4;             // ld_y is a multiple of 4 floats and y is 16-B aligned
+  if (n4 > 0) fill_nan_kernel<<<grid_for(n4, sm), TPB, 0, s>>>(reinterpret_cast<float4*>(y), n4);
+  if (n > 0) scatter_kernel<<<grid_for(n, sm), TPB, 0, s>>>(gid, day, val, n, row_of_group, gstart, step, y, ld_y, t_len);
+  return cudaGetLastError();
+}
+
+}  // namespace mmf

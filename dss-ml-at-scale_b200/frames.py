@@ -123,9 +123,9 @@ def pack_groups(pdf: pd.DataFrame, keys=DEFAULT_KEYS, date_col="Date", value_col
 
 
 # ---- the drop-in UDF ---------------------------------------------------------------------------
-def forecast_groups(pdf: pd.DataFrame, *, keys=DEFAULT_KEYS, date_col="Date", value_col="Demand",
+def forecast_groups(pdf, *, keys=DEFAULT_KEYS, date_col="Date", value_col="Demand",
                     freq="W-MON", horizon=FORECAST_HORIZON, mode="holdout", design="trend_season_exog",
-                    engine: ForecastEngine | None = None) -> pd.DataFrame:
+                    engine: ForecastEngine | None = None, pack: str = "host") -> pd.DataFrame:
     """Fit + forecast every group in ``pdf``; returns ``tuning_schema`` rows
     (keys..., Date, Demand, Demand_Fitted), groups in key order, dates ascending.
 
@@ -133,14 +133,27 @@ def forecast_groups(pdf: pd.DataFrame, *, keys=DEFAULT_KEYS, date_col="Date", va
     ``horizon`` grid rows, emit fitted + forecast values for every grid date, 02:484-494);
     ``mode="future"`` fits on everything and emits the ``horizon`` dates after the end
     (``Demand`` is NaN there).
+
+    ``pack="device"`` groups, sorts and re-grids the rows on the GPU (``packer.pack_table_device``: Arrow
+    buffers in, padded series out) instead of with pandas on the host; ``pdf`` may then be an Arrow table.
     """
     eng = engine or default_engine()
     keys = list(keys)
     fitted_col = value_col + "_Fitted"
     parts = []
-    for b in pack_groups(pdf, keys, date_col, value_col, freq):
+    if pack == "device":
+        from .packer import pack_table_device
+        buckets = pack_table_device(pdf, keys, date_col, value_col, freq, engine=eng)
+    elif pack == "host":
+        buckets = pack_groups(pdf, keys, date_col, value_col, freq)
+    else:
+        raise ValueError("pack must be 'host' or 'device'")
+    for b in buckets:
         out_days, pred_start, n_pred = eng.plan_calendar(b.start, b.t_len, freq, horizon, mode, design)
         pred = eng.fit_forecast(b.y, pred_start, n_pred)
+        if pack == "device":
+            pred = pred.cpu().numpy()
+            b.y = b.y.cpu().numpy()
         n = b.y.shape[0]
         frame = {k: np.repeat(b.key_frame[k].to_numpy(), n_pred) for k in keys}
         frame[date_col] = np.tile(out_days.astype("datetime64[ns]"), n)
@@ -169,7 +182,7 @@ def forecast_table(table, **kw):
         table = pa.Table.from_batches([table])
     keys = kw.get("keys", DEFAULT_KEYS)
     date_col, value_col = kw.get("date_col", "Date"), kw.get("value_col", "Demand")
-    out = forecast_groups(table.to_pandas(), **kw)
+    out = forecast_groups(table if kw.get("pack") == "device" else table.to_pandas(), **kw)
     return pa.Table.from_pandas(out, schema=tuning_schema(keys, date_col, value_col), preserve_index=False)
 
 

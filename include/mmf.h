@@ -132,6 +132,28 @@ int mmf_fit_forecast_bcast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t 
                                const uint64_t* out_ptrs, int32_t n_out, int32_t multimem, int64_t ld_out,
                                float* out_beta, int32_t* out_status);
 
+/* ---- device-side packer: long-format rows -> padded series on the GPU ------------------------------
+ * replaces the hash shuffle of repartition(n_tasks,"Product","SKU") + groupBy (02:525-526) and the per-group
+ * sort_values("Date") + set_index("Date").asfreq(freq) (02:422-423).  All pointers are DEVICE pointers holding
+ * the Arrow column buffers as they are; rows may arrive in any order.
+ *   hash_utf8 / hash_i32 : chain a utf8 (offsets+bytes) or dictionary-index key column into a 64-bit FNV-1a row
+ *                          hash (first != 0 starts a new hash, 0 continues `hash`)
+ *   group_codes          : dense group code per row (groups numbered in hash order), the first row of every
+ *                          group (to read its key values back) and the number of groups (host int, synchronises)
+ *   minmax               : first / last day of every group
+ *   scatter_f32          : y[row_of_group[g], (day - gstart[g]) / step] = value after a NaN fill; rows of groups with
+ *                          row_of_group < 0 (other calendar buckets) and off-grid dates are skipped            */
+int mmf_pack_hash_utf8(mmf_ctx* ctx, const int32_t* offsets, const uint8_t* data, int64_t n, uint64_t* hash,
+                       int32_t first);
+int mmf_pack_hash_i32(mmf_ctx* ctx, const int32_t* values, int64_t n, uint64_t* hash, int32_t first);
+int mmf_pack_group_codes(mmf_ctx* ctx, const uint64_t* hash, int64_t n, int32_t* gid, int32_t* first_row,
+                         int32_t* n_groups);
+int mmf_pack_minmax(mmf_ctx* ctx, const int32_t* gid, const int32_t* day, int64_t n, int32_t n_groups,
+                    int32_t* gmin, int32_t* gmax);
+int mmf_pack_scatter_f32(mmf_ctx* ctx, const int32_t* gid, const int32_t* day, const float* val, int64_t n,
+                         const int64_t* row_of_group, const int32_t* gstart, int32_t step, float* y, int64_t n_rows,
+                         int64_t ld_y, int32_t t_len);
+
 /* ---- host memory helpers (Arrow buffers -> one cudaMemcpyAsync) ---------- */
 int mmf_alloc_pinned(size_t bytes, void** out);
 int mmf_free_pinned(void* p);

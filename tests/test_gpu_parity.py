@@ -317,3 +317,74 @@ def test_holdout_on_tensor_cores_matches_oracle_and_warp(engines, n, t):
         outs[k] = pred
         assert res["stats"].kernel_used == ("warp" if k == "warp" else "tc")
     assert np.nanmax(np.abs(outs["auto"] - outs["warp"])) <= tolerance(y)
+
+
+# ---- device-side packer: Arrow buffers -> padded series on the GPU ---------------------
+def _long_frame(seed=0):
+    import pandas as pd
+    rng = np.random.default_rng(seed)
+    rows = []
+    for g in range(40):
+        start = dt.date(2021, 1, 4) + dt.timedelta(weeks=int(rng.integers(0, 3)))     # three different calendars
+        n = int(rng.integers(30, 60))
+        for i in range(n):
+            if rng.random() < 0.05:
+                continue                                                               # gaps
+            rows.append((f"prod{g % 7}", f"sku_{g:03d}", start + dt.timedelta(weeks=i), float(rng.normal(1000, 50))))
+    rows.append(("prod1", "sku_001", dt.date(2021, 2, 3), 123.0))                      # off-grid (a Wednesday)
+    df = pd.DataFrame(rows, columns=["Product", "SKU", "Date", "Demand"]).astype({"Demand": np.float32})
+    return df.sample(frac=1.0, random_state=seed).reset_index(drop=True)               # arbitrary row order
+
+
+def test_device_packer_equals_host_packer():
+    import pyarrow as pa
+    from mmf.packer import pack_table_device
+    df = _long_frame(3)
+    host = mmf.pack_groups(df, freq="W-MON", pinned=False)
+    for table in (pa.Table.from_pandas(df, preserve_index=False),                                    # utf8 keys
+                  pa.Table.from_pandas(df, preserve_index=False).set_column(
+                      0, "Product", pa.array(df["Product"]).dictionary_encode())):                    # dictionary key
+        dev = pack_table_device(table, freq="W-MON")
+        assert len(dev) == len(host)
+        for bd, bh in zip(dev, host):
+            assert (str(bd.start), bd.t_len) == (str(bh.start), bh.t_len)
+            assert bd.key_frame.values.tolist() == bh.key_frame.values.tolist()
+            assert bd.y.stride(0) % 4 == 0
+            assert np.array_equal(bd.y.cpu().numpy(), bh.y, equal_nan=True)
+
+
+def test_forecast_groups_with_device_packer_matches_host_path():
+    import pyarrow as pa
+    df = _long_frame(5)
+    kw = dict(freq="W-MON", horizon=8, mode="holdout")
+    a = mmf.forecast_groups(df, **kw)
+    b = mmf.forecast_groups(df, pack="device", **kw)
+    assert list(a.columns) == list(b.columns) and len(a) == len(b)
+    assert (a["SKU"].to_numpy() == b["SKU"].to_numpy()).all() and (a["Date"].to_numpy() == b["Date"].to_numpy()).all()
+    assert np.array_equal(a["Demand"].to_numpy(), b["Demand"].to_numpy(), equal_nan=True)
+    assert np.array_equal(a["Demand_Fitted"].to_numpy(), b["Demand_Fitted"].to_numpy(), equal_nan=True)
+    t = mmf.forecast_table(pa.Table.from_pandas(df, preserve_index=False), pack="device", **kw)
+    assert t.num_rows == len(a)
+
+
+def test_device_packer_large_daily():
+    """100k groups x 120 days = 12M long-format rows, shuffled: device packer == direct packed array."""
+    import pyarrow as pa
+    import torch
+    from mmf.packer import pack_table_device
+    n, t = 100_000, 120
+    y, start = mmf.synth.daily_store_item_demand(n, t, seed=77)
+    days = mmf.design.calendar_grid(start, t, "D").astype("datetime64[D]").astype(np.int32)
+    rng = np.random.default_rng(1)
+    perm = rng.permutation(n * t)
+    item = np.repeat(np.arange(n, dtype=np.int32), t)[perm]
+    table = pa.table({"store": pa.array((item % 50).astype(np.int32)), "item": pa.array(item),
+                      "date": pa.array(np.tile(days, n)[perm], type=pa.int32()).cast(pa.date32()),
+                      "sales": pa.array(y.reshape(-1)[perm])})
+    (b,) = pack_table_device(table, keys=("store", "item"), date_col="date", value_col="sales", freq="D", sort_keys=True)
+    assert b.t_len == t and b.y.shape == (n, t)
+    # sort_keys orders groups by (store, item); map back to item order
+    order = b.key_frame["item"].to_numpy().astype(np.int64)
+    got = torch.empty_like(b.y)
+    got[torch.as_tensor(order, device="cuda", dtype=torch.long)] = b.y
+    assert np.array_equal(got.cpu().numpy(), y)
