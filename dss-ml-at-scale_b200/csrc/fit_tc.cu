@@ -101,6 +101,7 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
   const int lane = threadIdx.x & 31;
 
   // ---- one-time setup
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.zero_next != nullptr) { a.zero_next[0] = 0u; a.zero_next[1] = 0u; }
   if (warp == WARP_MMA) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) {
@@ -224,12 +225,14 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
 #pragma unroll
       for (int q = 0; q < 8; ++q) v[q] = lds128(rowp + ((static_cast<uint32_t>(q) ^ sw) << 4));
       if (collect) {
-        float chk = 0.f;                                // 0 * x is NaN exactly when x is NaN or Inf
+        float2 chk2 = make_float2(0.f, 0.f);            // 0 * x is NaN exactly when x is NaN or Inf
+        const float2 zero2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          chk = fmaf(v[q].x, 0.f, chk); chk = fmaf(v[q].y, 0.f, chk);
-          chk = fmaf(v[q].z, 0.f, chk); chk = fmaf(v[q].w, 0.f, chk);
+          chk2 = fma_f32x2(make_float2(v[q].x, v[q].y), zero2, chk2);
+          chk2 = fma_f32x2(make_float2(v[q].z, v[q].w), zero2, chk2);
         }
+        const float chk = chk2.x + chk2.y;
         if (!(chk == 0.f)) {                            // rare: this row has a gap inside this chunk
           // branch-free substitution + a bit mask of the gap positions, then a short loop over the set bits
           unsigned gaps = 0u;
@@ -251,15 +254,17 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
         }
       }
       uint32_t hi[32], lo[32];
+      const float2 c2 = make_float2(c, c);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const float e[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          const float rr = e[w] - c;
-          const uint32_t h = __float_as_uint(rr) & 0xFFFFE000u;
-          hi[q * 4 + w] = h;
-          lo[q * 4 + w] = __float_as_uint(rr - __uint_as_float(h));
+        for (int hlf = 0; hlf < 2; ++hlf) {              // packed pairs: FADD2 for the centring and the residual
+          const float2 e = hlf ? make_float2(v[q].z, v[q].w) : make_float2(v[q].x, v[q].y);
+          const float2 rr = sub_f32x2(e, c2);
+          const uint32_t h0 = __float_as_uint(rr.x) & 0xFFFFE000u, h1 = __float_as_uint(rr.y) & 0xFFFFE000u;
+          const float2 l = sub_f32x2(rr, make_float2(__uint_as_float(h0), __uint_as_float(h1)));
+          hi[q * 4 + 2 * hlf] = h0;  hi[q * 4 + 2 * hlf + 1] = h1;
+          lo[q * 4 + 2 * hlf] = __float_as_uint(l.x);  lo[q * 4 + 2 * hlf + 1] = __float_as_uint(l.y);
         }
       }
       mbar_wait(bar_aempty(grp, aslot), aphase ^ 1u);   // MMAs that read this A slot have retired

@@ -225,6 +225,7 @@ __device__ __noinline__ int solve_masked(const DesignView& d, const ARows& A, co
 __global__ void __launch_bounds__(THREADS, 1)
 fit_warp_kernel(const DesignView d, const FitArgs a, const int smem_rows) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  asm volatile("griddepcontrol.wait;" ::: "memory");    // programmatic dependent launch: the producer kernel is done
   if (a.pending_count != nullptr && *a.pending_count == 0u) return;   // grid-uniform early exit
 
   float4* s_a4 = reinterpret_cast<float4*>(smem_raw);
@@ -459,8 +460,17 @@ cudaError_t launch_fit_warp(const DesignView& d, const FitArgs& a, int sm_count,
   int64_t blocks = (groups + WARPS - 1) / WARPS;
   const int64_t cap = (int64_t)sm_count * per_sm;
   if (blocks > cap) blocks = cap;
-  fit_warp_kernel<<<(unsigned)blocks, THREADS, smem, s>>>(d, a, smem_rows);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)blocks);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // launch latency hides under the producer
+  attr[0].val.programmaticStreamSerializationAllowed = a.only_pending ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, fit_warp_kernel, d, a, smem_rows);
 }
 
 }  // namespace mmf

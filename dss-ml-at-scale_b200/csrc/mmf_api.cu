@@ -104,7 +104,8 @@ struct mmf_ctx {
   bool own_stream = false;
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
-  uint32_t* d_pending = nullptr;       // [0] rows the tcgen05 kernel left PENDING, [1] solve records written
+  uint32_t* d_pending = nullptr;       // 2 ping-pong sets of {rows left PENDING, solve records queued}
+  int counter_set = 0;
   SolveRec* d_recs = nullptr;          // deferred masked series (grown on demand, capped)
   size_t recs_cap_bytes = 0;
   int64_t* d_rec_rows = nullptr;
@@ -189,21 +190,29 @@ int run_device(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, int32_t pr
     if (rc != MMF_OK) return rc;
     a.recs = ctx->d_recs;
     a.rec_rows = ctx->d_rec_rows;
-    a.rec_count = ctx->d_pending + 1;
     a.rec_cap = (uint32_t)cap;
   }
-  CU_TRY(cudaMemsetAsync(ctx->d_pending, 0, 2 * sizeof(uint32_t), s));
+  // counters: this call uses set `cs`; the tcgen05 kernel zeroes the other set for the next call, so the common
+  // path has no memset node (the warp-only path still clears its set explicitly)
+  const int cs = ctx->counter_set;
+  uint32_t* counters = ctx->d_pending + 2 * cs;
+  ctx->counter_set ^= 1;
+  if (may_mask) a.rec_count = counters + 1;
+  if (kernel == MMF_KERNEL_TC) a.zero_next = ctx->d_pending + 2 * (cs ^ 1);
+  else {
+    CU_TRY(cudaMemsetAsync(ctx->d_pending, 0, 4 * sizeof(uint32_t), s));
+  }
   if (kernel == MMF_KERNEL_TC) {
     TcLaunch tl;
     int rc = encode_2d(tl.tmap_y, y, (uint64_t)d.t_fit, (uint64_t)n, (uint64_t)ld_y * 4, 32, 128);
     if (rc != MMF_OK) return rc;
     memcpy(tl.tmap_at, ctx->plan.tmap_at, 128);
-    CU_TRY(launch_fit_tc(d, a, tl, ctx->d_pending, ctx->sm_count, s));
+    CU_TRY(launch_fit_tc(d, a, tl, counters, ctx->sm_count, s));
     ++*launches;
     if (may_mask) {
       FitArgs m = a;
       m.only_pending = 1;
-      m.pending_count = ctx->d_pending;
+      m.pending_count = counters;
       CU_TRY(launch_fit_warp(d, m, ctx->sm_count, s));
       CU_TRY(launch_solve_rows(d, m, ctx->sm_count, s));
       *launches += 2;
@@ -292,8 +301,8 @@ int mmf_create(const mmf_config* cfg, mmf_ctx** out) {
     cudaEventCreateWithFlags(&ctx->st[i].ev_comp, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->st[i].ev_d2h, cudaEventDisableTiming);
   }
-  if ((e = cudaMalloc(&ctx->d_pending, 2 * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
-  cudaMemset(ctx->d_pending, 0, 2 * sizeof(uint32_t));
+  if ((e = cudaMalloc(&ctx->d_pending, 4 * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
+  cudaMemset(ctx->d_pending, 0, 4 * sizeof(uint32_t));
   *out = ctx;
   return MMF_OK;
 }
@@ -509,7 +518,7 @@ int mmf_fit_forecast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, 
       CU_TRY(cudaEventElapsedTime(&stats->kernel_ms, ctx->ev_k0, ctx->ev_k1));
       stats->total_ms = stats->kernel_ms;
       uint32_t pend = 0;
-      CU_TRY(cudaMemcpy(&pend, ctx->d_pending, sizeof(pend), cudaMemcpyDeviceToHost));
+      CU_TRY(cudaMemcpy(&pend, ctx->d_pending + 2 * (ctx->counter_set ^ 1), sizeof(pend), cudaMemcpyDeviceToHost));
       stats->n_pending = (kernel_used == MMF_KERNEL_TC) ? pend : 0;
     }
   } else {

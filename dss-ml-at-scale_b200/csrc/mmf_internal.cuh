@@ -66,6 +66,7 @@ struct FitArgs {
   uint32_t rec_cap;         //   == n
   int32_t only_pending;     // 1: process only rows whose status == MMF_STATUS_PENDING
   const uint32_t* pending_count;  // nullable; if non-null and *pending_count == 0 the kernel exits at once
+  uint32_t* zero_next;      // nullable: 2 counters of the NEXT call's set, zeroed by the tcgen05 kernel (no memset node)
 };
 
 // warp-per-series CUDA-core kernel (general path)

@@ -20,6 +20,7 @@ __device__ __forceinline__ constexpr int tri(int i, int j) { return i * (i + 1) 
 
 __global__ void __launch_bounds__(THREADS, 2)
 solve_rows_kernel(const DesignView d, const FitArgs a) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");    // programmatic dependent launch: the producer kernels are done
   const uint32_t count = min(*a.rec_count, a.rec_cap);
   for (uint32_t i = blockIdx.x * THREADS + threadIdx.x; i < count; i += gridDim.x * THREADS) {
     const int64_t row = a.rec_rows[i];
@@ -133,8 +134,17 @@ cudaError_t launch_solve_rows(const DesignView& d, const FitArgs& a, int sm_coun
   const int64_t want = ((int64_t)a.rec_cap + THREADS - 1) / THREADS;
   const int64_t cap = (int64_t)sm_count * 8;
   const unsigned grid = (unsigned)(want < cap ? want : cap);
-  solve_rows_kernel<<<grid, THREADS, 0, s>>>(d, a);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // launch latency hides under the producer
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, solve_rows_kernel, d, a);
 }
 
 }  // namespace mmf
