@@ -87,7 +87,11 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
   uint16_t* s_nm = reinterpret_cast<uint16_t*>(smem + SmemLayout::nm);
   // series with gaps: substitute the centring constant for missing values (so the moments stay exact), record
   // where they were, and let the epilogue queue a SolveRec for solve_rows_kernel instead of a second pass
+#ifdef MMF_TC_NO_COLLECT
+  const bool collect = false;
+#else
   const bool collect = a.recs != nullptr && d.t_fit <= 65535;
+#endif
   const uint32_t s_bars = sbase + SmemLayout::bars;
   auto bar_full = [&](int s) { return s_bars + 8u * s; };
   auto bar_empty = [&](int s) { return s_bars + 8u * (STAGES + s); };
@@ -307,7 +311,11 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
     // Staged epilogue: the tile's forecasts are one contiguous block of the table (rows are dense), so they are
     // assembled in shared memory and leave as ONE bulk (TMA) store per destination -- full-size NVLink packets
     // for the peers' copies instead of 16-B stores scattered at a 112-B stride.
+#ifdef MMF_TC_NO_BULK
+    const bool bulk = false;
+#else
     const bool bulk = !a.skip_pred && vec_out && a.out_multimem != 1 && a.ld_out == a.n_pred && a.n_pred <= BULK_MAX_PRED;
+#endif
     const uint32_t s_ostage_u32 = smem_u32(s_ostage);
     int lt = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
