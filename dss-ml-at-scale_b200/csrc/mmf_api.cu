@@ -155,7 +155,8 @@ DesignView view_of(const Plan& p) {
 // Enqueue the fit for device-resident buffers on `s`.  status must be non-null.
 int run_device(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, int32_t pred_start, int32_t n_pred,
                float* out, int64_t ld_out, float* beta, int32_t* status, cudaStream_t s, int* launches,
-               int* kernel_used, float* const* out_more = nullptr, int n_out = 1, int multimem = 0) {
+               int* kernel_used, float* const* out_more = nullptr, int n_out = 1, int multimem = 0,
+               const SelectArgs* sel = nullptr) {
   const DesignView d = view_of(ctx->plan);
   FitArgs a{};
   a.y = y; a.n = n; a.ld_y = ld_y; a.pred_start = pred_start; a.n_pred = n_pred;
@@ -167,8 +168,11 @@ int run_device(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, int32_t pr
   int kernel = ctx->cfg.kernel;
   // Many prediction rows (the reference's "Demand_Fitted for every date", 02:484-494): fit kernels hand
   // gamma/c to predict_tc_kernel, which writes the [n, n_pred] table with TMA stores.
-  const bool many_pred = n_pred > 64 && kernel != MMF_KERNEL_WARP && n_out == 1 && !multimem && ld_out % 4 == 0 &&
-                         (reinterpret_cast<uintptr_t>(out) & 15u) == 0 && n <= (int64_t)0x7fffffff - 128;
+  const bool predict_ok = n_out == 1 && !multimem && ld_out % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0 &&
+                          n <= (int64_t)0x7fffffff - 128;
+  if (sel != nullptr && !predict_ok)
+    return fail(MMF_E_UNSUPPORTED, "model selection needs a 16-B aligned output with ld_out %% 4 == 0");
+  const bool many_pred = sel != nullptr || (n_pred > 64 && kernel != MMF_KERNEL_WARP && predict_ok);
   if (many_pred) {
     int rc = grow((void**)&ctx->d_gamma, &ctx->gamma_cap_bytes, (size_t)n * P * sizeof(float));
     if (rc == MMF_OK) rc = grow((void**)&ctx->d_c, &ctx->c_cap_bytes, (size_t)n * sizeof(float));
@@ -224,6 +228,10 @@ int run_device(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, int32_t pr
       CU_TRY(launch_solve_rows(d, a, ctx->sm_count, s));
       ++*launches;
     }
+  }
+  if (sel != nullptr) {
+    CU_TRY(launch_select(d, a, *sel, ctx->sm_count, s));
+    ++*launches;
   }
   if (many_pred) {
     PredictLaunch pl;
@@ -636,6 +644,43 @@ int mmf_fit_forecast_bcast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t 
   int launches = 0, kernel_used = 0;
   return run_device(ctx, y, n, ld_y, pred_start, n_pred, reinterpret_cast<float*>(out_ptrs[0]), ld_out, out_beta,
                     status, ctx->stream, &launches, &kernel_used, more, n_out, multimem);
+}
+
+int mmf_fit_select_forecast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, int32_t n_hold,
+                                const int32_t* candidates, int32_t n_cand, int32_t pred_start, int32_t n_pred,
+                                float* out_pred, int64_t ld_out, int32_t* out_choice, float* out_mse,
+                                int32_t* out_status) {
+  if (!ctx) return fail(MMF_E_INVALID, "ctx is NULL");
+  if (!ctx->plan.valid) return fail(MMF_E_NOPLAN, "mmf_plan_design has not been called");
+  const Plan& pl = ctx->plan;
+  if (n < 0 || (n > 0 && (!y || !out_pred))) return fail(MMF_E_INVALID, "bad y / out_pred / n");
+  if (!candidates || n_cand < 1 || n_cand > MMF_MAX_CAND) return fail(MMF_E_INVALID, "need 1..%d candidates", MMF_MAX_CAND);
+  for (int i = 0; i < n_cand; ++i)
+    if (candidates[i] < 1 || candidates[i] > P || (i > 0 && candidates[i] <= candidates[i - 1]))
+      return fail(MMF_E_INVALID, "candidates must be ascending column counts in [1,%d]", P);
+  if (n_hold < 1 || pl.t_fit + n_hold > pl.n_rows) return fail(MMF_E_INVALID, "held-out rows exceed the planned design");
+  if (ld_y < pl.t_fit + n_hold) return fail(MMF_E_INVALID, "y must hold the fit rows and the held-out rows");
+  if (n_pred < 1 || pred_start < 0 || (int64_t)pred_start + n_pred > pl.n_rows)
+    return fail(MMF_E_INVALID, "prediction rows outside the planned design");
+  if (ld_out < n_pred) return fail(MMF_E_INVALID, "ld_out < n_pred");
+  if (n == 0) return MMF_OK;
+  CU_TRY(cudaSetDevice(ctx->device));
+  if (!is_device_ptr(y) || !is_device_ptr(out_pred)) return fail(MMF_E_INVALID, "device buffers only");
+  int32_t* status = out_status;
+  if (!status) {
+    int rc = grow((void**)&ctx->d_status_scratch, &ctx->status_scratch_cap, (size_t)n * sizeof(int32_t));
+    if (rc != MMF_OK) return rc;
+    status = ctx->d_status_scratch;
+  }
+  SelectArgs sel{};
+  sel.n_hold = n_hold;
+  sel.n_cand = n_cand;
+  for (int i = 0; i < n_cand; ++i) sel.cand[i] = candidates[i];
+  sel.out_choice = out_choice;
+  sel.out_mse = out_mse;
+  int launches = 0, kernel_used = 0;
+  return run_device(ctx, y, n, ld_y, pred_start, n_pred, out_pred, ld_out, nullptr, status, ctx->stream, &launches,
+                    &kernel_used, nullptr, 1, 0, &sel);
 }
 
 // ---- device-side packer (pack.cu): every pointer is a device pointer, work is enqueued on the ctx stream

@@ -96,6 +96,17 @@ cudaError_t launch_fit_tc(const DesignView& d, const FitArgs& a, const TcLaunch&
                           uint32_t* pending_count, int sm_count, cudaStream_t s);
 bool fit_tc_supported(const DesignView& d, const FitArgs& a, const char** why);
 
+// per-series model selection by hold-out MSE over nested whitened designs (select.cu)
+constexpr int MMF_MAX_CAND = 8;
+struct SelectArgs {
+  int32_t n_hold;                 // held-out rows: design rows [t_fit, t_fit + n_hold), y columns likewise
+  int32_t n_cand;
+  int32_t cand[MMF_MAX_CAND];     // ascending numbers of leading whitened columns, last == full model
+  int32_t* out_choice;            // nullable [n]: chosen number of columns (0 for empty series)
+  float* out_mse;                 // nullable [n]: hold-out MSE of the chosen model
+};
+cudaError_t launch_select(const DesignView& d, const FitArgs& a, const SelectArgs& sel, int sm_count, cudaStream_t s);
+
 // device-side packer (pack.cu)
 cudaError_t pack_hash_utf8(const int32_t* offsets, const uint8_t* data, int64_t n, uint64_t* h, int first, int sm,
                            cudaStream_t s);

@@ -220,6 +220,30 @@ class ForecastEngine:
         return res
 
 
+    def fit_select_forecast(self, y, n_hold: int, candidates=(1, 3, 9, 13, 16), pred_start: int = 0,
+                            n_pred: int | None = None):
+        """Per-series model selection on the device (reference: the hyperopt loop + refit, 02:435-488).
+        ``y`` [n, >= t_fit + n_hold] CUDA tensor: rows [0,t_fit) are fit, the next ``n_hold`` score the nested
+        candidate designs (first ``m`` whitened columns); the winner predicts rows [pred_start, +n_pred).
+        Returns ``{"pred", "choice", "mse", "status"}`` (torch tensors)."""
+        import torch
+        if self.t_fit is None:
+            raise RuntimeError("plan()/plan_calendar() must be called first")
+        yp, n, t_have, ld_y = _describe(y, "y")
+        if not (_is_torch(y) and y.is_cuda and y.dtype == torch.float32):
+            raise ValueError("y must be a float32 CUDA tensor")
+        n_pred = self.n_rows - pred_start if n_pred is None else n_pred
+        self.set_stream(torch.cuda.current_stream(y.device).cuda_stream)
+        out = torch.empty((n, (n_pred + 3) & ~3), dtype=torch.float32, device=y.device)[:, :n_pred]
+        choice = torch.empty(n, dtype=torch.int32, device=y.device)
+        mse = torch.empty(n, dtype=torch.float32, device=y.device)
+        status = torch.empty(n, dtype=torch.int32, device=y.device)
+        cand = (C.c_int32 * len(candidates))(*[int(c) for c in candidates])
+        N.check(self._lib.mmf_fit_select_forecast_f32(self._h, yp, n, ld_y, int(n_hold), cand, len(candidates),
+                                                      int(pred_start), int(n_pred), out.data_ptr(), out.stride(0),
+                                                      choice.data_ptr(), mse.data_ptr(), status.data_ptr()))
+        return {"pred": out, "choice": choice, "mse": mse, "status": status}
+
     def fit_forecast_bcast(self, y, pred_start: int, n_pred: int, out_ptrs, ld_out: int, multimem: int = 0,
                            status=None):
         """Fit the rows of the CUDA tensor ``y`` and store every forecast row to all ``out_ptrs``

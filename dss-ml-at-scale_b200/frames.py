@@ -125,7 +125,7 @@ def pack_groups(pdf: pd.DataFrame, keys=DEFAULT_KEYS, date_col="Date", value_col
 # ---- the drop-in UDF ---------------------------------------------------------------------------
 def forecast_groups(pdf, *, keys=DEFAULT_KEYS, date_col="Date", value_col="Demand",
                     freq="W-MON", horizon=FORECAST_HORIZON, mode="holdout", design="trend_season_exog",
-                    engine: ForecastEngine | None = None, pack: str = "host") -> pd.DataFrame:
+                    engine: ForecastEngine | None = None, pack: str = "host", select=None) -> pd.DataFrame:
     """Fit + forecast every group in ``pdf``; returns ``tuning_schema`` rows
     (keys..., Date, Demand, Demand_Fitted), groups in key order, dates ascending.
 
@@ -133,6 +133,10 @@ def forecast_groups(pdf, *, keys=DEFAULT_KEYS, date_col="Date", value_col="Deman
     ``horizon`` grid rows, emit fitted + forecast values for every grid date, 02:484-494);
     ``mode="future"`` fits on everything and emits the ``horizon`` dates after the end
     (``Demand`` is NaN there).
+
+    ``select=(1, 3, 9, 13, 16)`` (holdout mode only) turns on the per-series model selection that stands in for the
+    reference's hyperopt loop (02:435-481): nested designs on the first ``m`` whitened columns are scored by their
+    MSE over the held-out rows and the winner produces ``Demand_Fitted`` (``ForecastEngine.fit_select_forecast``).
 
     ``pack="device"`` groups, sorts and re-grids the rows on the GPU (``packer.pack_table_device``: Arrow
     buffers in, padded series out) instead of with pandas on the host; ``pdf`` may then be an Arrow table.
@@ -150,10 +154,20 @@ def forecast_groups(pdf, *, keys=DEFAULT_KEYS, date_col="Date", value_col="Deman
         raise ValueError("pack must be 'host' or 'device'")
     for b in buckets:
         out_days, pred_start, n_pred = eng.plan_calendar(b.start, b.t_len, freq, horizon, mode, design)
-        pred = eng.fit_forecast(b.y, pred_start, n_pred)
-        if pack == "device":
+        if select is not None:
+            if mode != "holdout":
+                raise ValueError("select= needs mode='holdout' (the held-out rows score the candidates)")
+            from .engine import device_packed
+            yd = b.y if pack == "device" else device_packed(b.y)
+            pred = eng.fit_select_forecast(yd, horizon, tuple(select), pred_start, n_pred)["pred"]
             pred = pred.cpu().numpy()
-            b.y = b.y.cpu().numpy()
+            if pack == "device":
+                b.y = b.y.cpu().numpy()
+        else:
+            pred = eng.fit_forecast(b.y, pred_start, n_pred)
+            if pack == "device":
+                pred = pred.cpu().numpy()
+                b.y = b.y.cpu().numpy()
         n = b.y.shape[0]
         frame = {k: np.repeat(b.key_frame[k].to_numpy(), n_pred) for k in keys}
         frame[date_col] = np.tile(out_days.astype("datetime64[ns]"), n)

@@ -132,6 +132,17 @@ int mmf_fit_forecast_bcast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t 
                                const uint64_t* out_ptrs, int32_t n_out, int32_t multimem, int64_t ld_out,
                                float* out_beta, int32_t* out_status);
 
+/* ---- per-series model selection on the device ------------------------------------------------------
+ * GPU analogue of the per-group hyperopt loop (02:435-469) + final refit/predict (02:472-488): the planned design
+ * is fit on rows [0,t_fit); the candidates are the nested models made of the first candidates[k] whitened columns;
+ * each is scored by its MSE over the held-out rows [t_fit, t_fit+n_hold) of y; the best one (first minimum) produces
+ * out_pred for rows [pred_start, pred_start+n_pred).  Device buffers only, enqueue-only.
+ * out_choice[n] (nullable): chosen number of columns; out_mse[n] (nullable): its hold-out MSE.                  */
+int mmf_fit_select_forecast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, int32_t n_hold,
+                                const int32_t* candidates, int32_t n_cand, int32_t pred_start, int32_t n_pred,
+                                float* out_pred, int64_t ld_out, int32_t* out_choice, float* out_mse,
+                                int32_t* out_status);
+
 /* ---- device-side packer: long-format rows -> padded series on the GPU ------------------------------
  * replaces the hash shuffle of repartition(n_tasks,"Product","SKU") + groupBy (02:525-526) and the per-group
  * sort_values("Date") + set_index("Date").asfreq(freq) (02:422-423).  All pointers are DEVICE pointers holding

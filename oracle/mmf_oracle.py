@@ -315,3 +315,42 @@ def fanout_apply(pdf, func, keys):
 
     parts = [func(g.copy()) for _, g in pdf.groupby(list(keys), sort=True)]
     return pd.concat(parts, ignore_index=True)
+
+
+# ----------------------------------------------------------------------------
+# per-series model selection (the engine's analogue of the reference's hyperopt loop, 02:435-488)
+# ----------------------------------------------------------------------------
+def select_forecast_packed(y: np.ndarray, X: np.ndarray, t_fit: int, n_hold: int, candidates, pred_start: int,
+                           n_pred: int):
+    """Candidates = nested models on the first ``m`` whitened columns (``m`` in ``candidates``, ascending).
+    Spec: fit the full whitened model on the observed rows of [0,t_fit); candidate m keeps
+    the first m whitened coefficients (for a gap-free series that IS the least-squares fit of the sub-model, the
+    basis being orthonormal on the calendar); score = MSE over the observed held-out rows [t_fit,t_fit+n_hold);
+    the first minimum wins (no observed held-out row: the last candidate); predict with the winner.
+    Returns pred [N,n_pred], choice [N] (0 for empty series), mse [N], status [N]."""
+    y = np.asarray(y, dtype=np.float64)
+    X = np.asarray(X, dtype=np.float64)
+    _, status, gamma, _ = fit_forecast_packed(y[:, :t_fit], X, t_fit, 0, 1, return_gamma=True)
+    W, _ = whiten(X[:t_fit])
+    A = X @ W
+    A_hold = A[t_fit:t_fit + n_hold]
+    n = y.shape[0]
+    pred = np.full((n, n_pred), np.nan)
+    choice = np.zeros(n, dtype=np.int32)
+    mse = np.full(n, np.nan)
+    for i in range(n):
+        if status[i] == 1:
+            continue
+        yh = y[i, t_fit:t_fit + n_hold]
+        obs = np.isfinite(yh)
+        best_m, best = candidates[-1], np.nan
+        if obs.any():
+            scores = []
+            for m in candidates:
+                e = yh[obs] - A_hold[obs][:, :m] @ gamma[i, :m]
+                scores.append(float(np.mean(e * e)))
+            k = int(np.argmin(scores))                   # first minimum
+            best_m, best = candidates[k], scores[k]
+        choice[i], mse[i] = best_m, best
+        pred[i] = A[pred_start:pred_start + n_pred, :best_m] @ gamma[i, :best_m]
+    return pred, choice, mse, status

@@ -388,3 +388,53 @@ def test_device_packer_large_daily():
     got = torch.empty_like(b.y)
     got[torch.as_tensor(order, device="cuda", dtype=torch.long)] = b.y
     assert np.array_equal(got.cpu().numpy(), y)
+
+
+# ---- on-device model selection: the hyperopt-loop analogue ---------------------------------
+def test_model_selection_on_device_matches_oracle(engines):
+    n, t, h = 600, 400, 28
+    rng = np.random.default_rng(9)
+    y, start = mmf.synth.daily_store_item_demand(n, t, seed=61)
+    y[:100] = np.round(5000 + rng.normal(0, 30, (100, t)))          # pure level + noise: small models should win
+    tt = np.arange(t)
+    y[100:200] = np.round(3000 + 4.0 * tt[None, :] + rng.normal(0, 20, (100, t)))   # level + trend
+    y[5, 50:80] = np.nan                                             # gaps in the fit window
+    y[6, t - 10:t - 3] = np.nan                                      # gaps in the held-out window
+    y[7, t - h:] = np.nan                                            # nothing held out is observed -> full model
+    y[8, :] = np.nan                                                 # empty
+    cands = (1, 3, 9, 13, 16)
+    grid = O.calendar_grid(start, t, "D")
+    X = O.design_matrix(grid, t - h)
+    want, wchoice, wmse, wst = O.select_forecast_packed(y, X, t - h, h, cands, 0, t)
+    eng = engines["auto"]
+    eng.plan_calendar(start, t, "D", h, "holdout")
+    res = eng.fit_select_forecast(mmf.device_packed(y), h, cands, 0, t)
+    import torch
+    torch.cuda.synchronize()
+    pred, choice, mse, st = (res[k].cpu().numpy() for k in ("pred", "choice", "mse", "status"))
+    assert np.array_equal(st, wst)
+    assert choice[8] == 0 and np.isnan(pred[8]).all() and choice[7] == 16
+    # the choice may legitimately differ only where two candidates score within fp32 noise of each other
+    same = choice == wchoice
+    assert same.mean() > 0.97
+    ok = same & (wst != 1)
+    assert np.abs(pred[ok] - want[ok]).max() <= tolerance(y)
+    assert np.allclose(mse[ok & np.isfinite(wmse)], wmse[ok & np.isfinite(wmse)], rtol=2e-3, atol=1e-2)
+    assert (choice[:100] <= 3).mean() > 0.5 and (choice[100:200] <= 9).mean() > 0.5      # simple series -> small models
+
+
+def test_forecast_groups_with_selection():
+    df = mmf.synth.reference_weekly_demand(n_skus=2)
+    full = mmf.forecast_groups(df)
+    sel = mmf.forecast_groups(df, select=(1, 3, 13, 16))
+    sel_dev = mmf.forecast_groups(df, select=(1, 3, 13, 16), pack="device")
+    assert list(sel.columns) == list(full.columns) and len(sel) == len(full)
+    assert np.array_equal(sel["Demand_Fitted"].to_numpy(), sel_dev["Demand_Fitted"].to_numpy())
+    want = O.fanout_apply(df, O.build_tune_and_score_model, ("Product", "SKU"))          # full model, for scale only
+    assert np.isfinite(sel["Demand_Fitted"].to_numpy()).all()
+    # the selected model can only do better (or equal) on the held-out 40 weeks than ... itself being a candidate:
+    def hold_mse(frame):
+        e = (frame["Demand"] - frame["Demand_Fitted"]).to_numpy().reshape(-1, 157)[:, -40:]
+        return (e * e).mean(axis=1)
+    assert (hold_mse(sel) <= hold_mse(full) * (1 + 1e-4)).all()
+    assert len(want) == len(sel)

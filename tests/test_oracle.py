@@ -183,3 +183,21 @@ def test_udf_contract_on_reference_data():
     fut = O.build_tune_and_score_model(one, mode="future", horizon=8)
     assert len(fut) == 8 and fut["Demand"].isna().all()
     assert fut["Date"].iloc[0] == dt.date(2021, 7, 26)
+
+
+def test_select_truncation_equals_refitting_nested_models():
+    """For a gap-free series the candidate 'first m whitened columns' equals the least-squares refit on the first m
+    raw design columns -- the property the device-side selection relies on."""
+    grid = O.calendar_grid(dt.date(2019, 1, 1), 300, "D")
+    X = O.design_matrix(grid, 272)
+    rng = np.random.default_rng(4)
+    t = np.arange(300.0)
+    y = 1000 + 2 * t + 50 * np.sin(2 * np.pi * t / 7) + rng.normal(0, 5, 300)
+    pred, choice, mse, st = O.select_forecast_packed(y[None], X, 272, 28, (1, 3, 9, 13, 16), 0, 300)
+    assert st[0] == 0 and choice[0] in (9, 13, 16)
+    m = int(choice[0])
+    ref = O.lstsq_reference(y[:272], X[:272, :m], X[:, :m])
+    assert np.abs(pred[0] - ref).max() < 1e-6
+    # a pure constant series: every candidate scores ~0, the first (smallest) one wins
+    pred, choice, mse, _ = O.select_forecast_packed(np.full((1, 300), 7.0), X, 272, 28, (1, 3, 9, 13, 16), 0, 300)
+    assert choice[0] == 1 and np.abs(pred - 7.0).max() < 1e-9
