@@ -9,7 +9,7 @@ into padded device buffers and fitted by hand-written sm_100a kernels in ``libmm
 The directory name is not a Python identifier; import it as ``import mmf`` (alias
 package at the repo root) or ``importlib.import_module("dss-ml-at-scale_b200")``.
 """
-from . import design, synth, sharding, packer               # noqa: F401
+from . import design, synth, sharding, packer, sink         # noqa: F401
 from ._native import LIB_PATH, MmfError, device_count, load as load_library   # noqa: F401
 from .engine import (ForecastEngine, Stats, alloc_packed, default_engine, device_packed, forecast_packed,
                      pinned_empty)  # noqa: F401

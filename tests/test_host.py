@@ -87,3 +87,25 @@ def test_all_gather_world2_gloo():
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "GLOO_OK rank 0" in r.stdout and "GLOO_OK rank 1" in r.stdout
+
+
+def test_sink_roundtrip(tmp_path):
+    """the forecast table written with tuning_schema (02:498-506, sink 02:539-552)."""
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    df = pd.DataFrame({"Product": ["a"] * 3 + ["b"] * 3, "SKU": ["s1"] * 3 + ["s2"] * 3,
+                       "Date": [dt.date(2021, 1, 4) + dt.timedelta(weeks=i) for i in range(3)] * 2,
+                       "Demand": np.array([1, 2, np.nan, 4, 5, 6], dtype=np.float32),
+                       "Demand_Fitted": np.arange(6, dtype=np.float32)})
+    path = mmf.sink.write_forecasts(df, str(tmp_path / "out" / "forecasts.parquet"))
+    meta = pq.read_schema(path)
+    assert meta.names == ["Product", "SKU", "Date", "Demand", "Demand_Fitted"]
+    assert pa.types.is_dictionary(meta.field("Product").type) and meta.field("Date").type == pa.date32()
+    back = mmf.sink.read_forecasts(path)
+    assert back["SKU"].tolist() == df["SKU"].tolist() and back["Date"].tolist() == df["Date"].tolist()
+    assert np.array_equal(back["Demand_Fitted"].to_numpy(), df["Demand_Fitted"].to_numpy())
+    assert np.isnan(back["Demand"].iloc[2])
+    mmf.sink.write_forecasts(df.iloc[:3], path)                       # overwrite
+    assert len(mmf.sink.read_forecasts(path)) == 3
+    with pytest.raises(FileExistsError):
+        mmf.sink.write_forecasts(df, path, mode="error")
