@@ -74,6 +74,24 @@ __device__ __forceinline__ float dot16(const float* __restrict__ arow, const flo
   return s;
 }
 
+// Centring constant of a series: its first finite value among the first 8 (any constant works -- the intercept
+// absorbs it exactly -- it only has to be near the series' level and identical in every warp role that uses it).
+// NaN when all 8 are missing: the row then takes the general pass.
+__device__ __forceinline__ float centring_constant(const float* __restrict__ yrow, int t_fit) {
+  float v[8];
+  if (t_fit >= 8) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(yrow)), b = __ldg(reinterpret_cast<const float4*>(yrow) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = i < t_fit ? __ldg(yrow + i) : __int_as_float(0x7fc00000);
+  }
+  float c = v[7];
+#pragma unroll
+  for (int i = 6; i >= 0; --i) c = ((__float_as_uint(v[i]) & 0x7f800000u) != 0x7f800000u) ? v[i] : c;
+  return c;
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
 fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const FitArgs a,
               uint32_t* __restrict__ pending_count, const int n_tiles, const int n_chunks) {
@@ -213,7 +231,7 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
     while (ch >= n_chunks && tile < n_tiles) { ch -= n_chunks; tile += gridDim.x; }   // n_chunks == 1 corner
     auto load_c = [&](int tl_) -> float {
       const int64_t row = (int64_t)tl_ * TILE_M + r;
-      return (d.has_constant && tl_ < n_tiles && row < a.n) ? __ldg(a.y + row * a.ld_y) : 0.f;
+      return (d.has_constant && tl_ < n_tiles && row < a.n) ? centring_constant(a.y + row * a.ld_y, d.t_fit) : 0.f;
     };
     auto finite = [](float x) { return (__float_as_uint(x) & 0x7f800000u) != 0x7f800000u; };
     float c = load_c(tile);
@@ -322,7 +340,7 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
       const int ab = lt & 1;
       const int64_t row = (int64_t)tile * TILE_M + r;
       const bool live = row < a.n;
-      float c = (d.has_constant && live) ? __ldg(a.y + row * a.ld_y) : 0.f;   // issued before the wait
+      float c = (d.has_constant && live) ? centring_constant(a.y + row * a.ld_y, d.t_fit) : 0.f;   // issued before the wait
       mbar_wait(bar_accfull(ab), (lt >> 1) & 1);
       tc_fence_after();
       uint32_t acc[32];
