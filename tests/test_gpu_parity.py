@@ -438,3 +438,13 @@ def test_forecast_groups_with_selection():
         return (e * e).mean(axis=1)
     assert (hold_mse(sel) <= hold_mse(full) * (1 + 1e-4)).all()
     assert len(want) == len(sel)
+
+
+def test_long_horizon_future_mode_uses_predict_kernel(engines):
+    """horizon > 64 in future mode: fit kernels + predict_tc_kernel, against the oracle and the warp kernel."""
+    y, start = mmf.synth.daily_store_item_demand(700, 500, seed=88)
+    want, _ = _oracle(y, start, "D", 120, "future")
+    for k in ("auto", "warp"):
+        pred, status, _ = _run(engines[k], y, start, "D", 120, "future")
+        assert pred.shape == (700, 120) and (status == 0).all()
+        assert np.abs(pred - want).max() <= tolerance(y), k
