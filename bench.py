@@ -216,7 +216,16 @@ def run_ours(args):
     sym = None
     if world > 1 and args.gather != "nccl":
         from mmf.sharding import SymmetricTable
-        sym = SymmetricTable(n, h, dev, mode=args.gather)
+        try:
+            sym = SymmetricTable(n, h, dev, mode=args.gather)
+            ok = torch.ones(1, device=dev)
+        except Exception as exc:                          # no NVLink symmetric memory on this box
+            sym, ok = None, torch.zeros(1, device=dev)
+            print(f"# rank {rank}: symmetric memory unavailable ({exc!r}); falling back to NCCL all_gather", file=sys.stderr)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)         # all ranks take the same path
+        if float(ok[0]) < 1.0:
+            sym = None
+    if sym is not None:
         table = sym.table
         gather = "fused-" + args.gather
     else:
