@@ -448,3 +448,15 @@ def test_long_horizon_future_mode_uses_predict_kernel(engines):
         pred, status, _ = _run(engines[k], y, start, "D", 120, "future")
         assert pred.shape == (700, 120) and (status == 0).all()
         assert np.abs(pred - want).max() <= tolerance(y), k
+
+
+@pytest.mark.parametrize("horizon", [1, 7, 30, 40, 64])
+def test_epilogue_store_paths_for_various_horizons(engines, horizon):
+    """bulk-store epilogue (n_pred % 4 == 0, <= 28), vectorised stores (<= 64), scalar stores (odd n_pred)."""
+    y, start = mmf.synth.daily_store_item_demand(517, 300, seed=500 + horizon)
+    y[11, 100:130] = np.nan
+    want, wst = _oracle(y, start, "D", horizon, "future")
+    for k in ("auto", "warp"):
+        pred, status, _ = _run(engines[k], y, start, "D", horizon, "future")
+        assert pred.shape == (517, horizon) and np.array_equal(status, wst)
+        assert np.abs(pred - want).max() <= tolerance(y), (k, horizon)
