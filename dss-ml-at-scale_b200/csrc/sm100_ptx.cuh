@@ -89,6 +89,24 @@ __device__ __forceinline__ void tma_load_2d_x2_elect(uint32_t bar, uint32_t tx_b
       : "memory");
 }
 
+// split form: arm the barrier, then issue loads separately (lets the producer order its loads freely)
+__device__ __forceinline__ void mbar_expect_tx_elect(uint32_t bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
+      ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_issue_2d_elect(uint32_t bar, uint32_t dst, const void* tmap, int32_t c0, int32_t c1,
+                                                   uint64_t hint) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%1], [%2, {%3, %4}], [%0], %5;\n\t}"
+      ::"r"(bar), "r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_2d_elect(uint32_t bar, uint32_t tx_bytes, uint32_t dst, const void* tmap,
                                                   int32_t c0, int32_t c1, uint64_t hint) {
   asm volatile(

@@ -261,6 +261,43 @@ __global__ void __launch_bounds__(64, 1) tma_read_kernel(const __grid_constant__
   }
 }
 
+// same, but each stage takes TWO adjacent boxes of the same rows (64 t = 256 contiguous bytes per row)
+__global__ void __launch_bounds__(64, 1) tma_read2_kernel(const __grid_constant__ Maps maps, int n_tiles, int n_chunks2,
+                                                         float* __restrict__ sink) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  constexpr int ST = 5;
+  const uint32_t s_y = smem_u32(smem);
+  const uint32_t bars = s_y + ST * 32768;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < ST; ++i) { mbar_init(bars + 8 * i, 1); mbar_init(bars + 8 * (ST + i), 1); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  int stage = 0; uint32_t phase = 0;
+  if (warp == 0) {
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+      for (int ch = 0; ch < n_chunks2; ++ch) {
+        mbar_wait(bars + 8 * (ST + stage), phase ^ 1u);
+        tma_load_2d_x2_elect(bars + 8 * stage, 32768, s_y + stage * 32768, maps.a, ch * 64, tile * 128, L2_EVICT_FIRST,
+                             s_y + stage * 32768 + 16384, maps.a, ch * 64 + 32, tile * 128, L2_EVICT_FIRST);
+        if (++stage == ST) { stage = 0; phase ^= 1u; }
+      }
+  } else {
+    float acc = 0.f;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+      for (int ch = 0; ch < n_chunks2; ++ch) {
+        mbar_wait(bars + 8 * stage, phase);
+        acc += lds128(s_y + stage * 32768 + lane * 16).x;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + 8 * (ST + stage));
+        if (++stage == ST) { stage = 0; phase ^= 1u; }
+      }
+    if (acc == 123.456f) sink[0] = acc;
+  }
+}
+
 __global__ void __launch_bounds__(512) ldg_read_kernel(const float4* __restrict__ p, size_t n4, float* __restrict__ sink) {
   float acc = 0.f;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -389,6 +426,16 @@ int main() {
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         if (rep == 2) printf("TMA read stream, grid %d: %.3f ms, %.0f GB/s (4*1095 B per row counted)\n", grid, ms, n * 1095.0 * 4 / ms / 1e6);
       }
+    }
+    CK(cudaFuncSetAttribute(tma_read2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * 32768 + 2048));
+    for (int rep = 0; rep < 3; ++rep) {
+      cudaEventRecord(e0);
+      tma_read2_kernel<<<148, 64, 5 * 32768 + 2048>>>(m2, (int)((n + 127) / 128), 18, sink);
+      cudaEventRecord(e1);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("tma_read2_kernel failed: %s\n", cudaGetErrorString(e)); return 3; }
+      float ms; cudaEventElapsedTime(&ms, e0, e1);
+      if (rep == 2) printf("TMA read stream, 2 adjacent boxes per stage (64 t), grid 148: %.3f ms, %.0f GB/s\n", ms, n * 1095.0 * 4 / ms / 1e6);
     }
     for (int rep = 0; rep < 3; ++rep) {
       cudaEventRecord(e0);
