@@ -354,3 +354,31 @@ def select_forecast_packed(y: np.ndarray, X: np.ndarray, t_fit: int, n_hold: int
         choice[i], mse[i] = best_m, best
         pred[i] = A[pred_start:pred_start + n_pred, :best_m] @ gamma[i, :best_m]
     return pred, choice, mse, status
+
+
+# ----------------------------------------------------------------------------
+# C restatement (oracle/mmf_oracle_c.c, pthreads): the fair multi-core CPU baseline
+# ----------------------------------------------------------------------------
+def fit_forecast_packed_c(y: np.ndarray, X: np.ndarray, t_fit: int, pred_start: int, n_pred: int, n_threads: int = 0,
+                          return_threads: bool = False):
+    """Same contract as :func:`fit_forecast_packed`, computed by ``libmmf_oracle.so`` (float64 accumulation, one
+    pass per series, all host cores).  ``y`` float32 [N, ld]."""
+    import ctypes as C
+    import os
+
+    lib = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmmf_oracle.so"))
+    y = np.ascontiguousarray(y, dtype=np.float32)
+    W, kept = whiten(np.asarray(X, dtype=np.float64)[:t_fit])
+    A = np.ascontiguousarray(np.asarray(X, dtype=np.float64) @ W)
+    kept32 = np.ascontiguousarray(kept.astype(np.int32))
+    n = y.shape[0]
+    out = np.empty((n, n_pred), dtype=np.float64)
+    status = np.empty(n, dtype=np.int32)
+    lib.mmf_oracle_fit_forecast.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                            C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]
+    lib.mmf_oracle_fit_forecast.restype = C.c_int
+    used = lib.mmf_oracle_fit_forecast(y.ctypes.data, n, y.strides[0] // 4, t_fit, A.ctypes.data, kept32.ctypes.data,
+                                       pred_start, n_pred, out.ctypes.data, status.ctypes.data, n_threads)
+    if return_threads:
+        return out, status, int(used)
+    return out, status

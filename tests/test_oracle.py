@@ -220,3 +220,26 @@ def test_bridge_to_reference_model_family_statsmodels():
     fc = fitted.predict(start=score.index.min(), end=score.index.max(), exog=exo.iloc[117:])
     ours = O.build_tune_and_score_model(one, design="exog_only")
     assert np.abs(fc.to_numpy() - ours["Demand_Fitted"].to_numpy()[117:]).max() <= 1e-3 * float(one["Demand"].max())
+
+
+def test_c_restatement_equals_numpy_oracle(oracle_golden):
+    """oracle/mmf_oracle_c.c (the multi-core CPU baseline of bench.py) against the NumPy oracle, incl. gaps,
+    an empty row and a rank-deficient mask."""
+    import subprocess, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-C", os.path.join(root, "oracle")], check=True, capture_output=True)
+    y = oracle_golden["daily365_y"].copy()
+    y[0, :] = np.nan
+    y[1, :] = np.nan; y[1, 40] = 3.0
+    grid = O.calendar_grid(oracle_golden["daily365_start"][0].astype("datetime64[D]"), 365 + 28, "D")
+    X = O.design_matrix(grid, 365)
+    want, wst = O.fit_forecast_packed(y, X, 365, 365, 28)
+    got, st = O.fit_forecast_packed_c(y, X, 365, 365, 28)
+    assert np.array_equal(st, wst)
+    ok = wst != 1
+    assert np.isnan(got[~ok]).all() and np.abs(got[ok] - want[ok]).max() < 1e-8
+    y2 = oracle_golden["daily1095_y"]
+    grid = O.calendar_grid(oracle_golden["daily1095_start"][0].astype("datetime64[D]"), 1095, "D")
+    Xh = O.design_matrix(grid, 1067)
+    got, _ = O.fit_forecast_packed_c(y2, Xh, 1067, 0, 1095)
+    assert np.abs(got - oracle_golden["daily1095_holdout"]).max() < 1e-7
