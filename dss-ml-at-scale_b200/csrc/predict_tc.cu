@@ -7,7 +7,8 @@
 //   A operand  gamma tile [128 series x 16] (fp32 split hi/lo, written once per tile with tcgen05.st)  -> TMEM
 //   B operand  prediction rows of the whitened design, [128 t x 16] K-major tiles (hi and lo), TMA, 64-B swizzle
 //   D          [128 series x 128 t] fp32 in TMEM, double buffered:  hi*Bhi + hi*Blo + lo*Bhi  (fp32-grade)
-//   epilogue   tcgen05.ld -> + c -> 128-B-swizzled shared tiles -> TMA 2-D stores (clipped at n / n_pred)
+//   epilogue   two warp groups on alternate chunks (one per accumulator / staging buffer): tcgen05.ld -> + c ->
+//              128-B-swizzled shared tiles -> TMA 2-D stores (clipped at n / n_pred)
 // Bound: HBM writes, 4*n_pred bytes per series.
 #include "mmf_internal.cuh"
 #include "sm100_ptx.cuh"
@@ -24,8 +25,8 @@ constexpr int B_TILE_BYTES = TN * P * 4;      // 8192 (hi) ; same for lo
 constexpr int B_STAGE_BYTES = 2 * B_TILE_BYTES;
 constexpr int OUT_SUB_BYTES = TILE_M * 32 * 4;          // one {32 t x 128 series} store box: 16384
 constexpr int OUT_STAGE_BYTES = (TN / 32) * OUT_SUB_BYTES;   // 65536
-constexpr int THREADS = 320;
-constexpr int WARP_LOAD0 = 4, WARP_PROD = 8, WARP_MMA = 9;
+constexpr int THREADS = 448;
+constexpr int WARP_LOAD0 = 8, WARP_PROD = 12, WARP_MMA = 13;     // warps 0-3 / 4-7: two epilogue groups
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t D_COL0 = 0;                // 2 x 128 accumulator columns
 constexpr uint32_t A_COL0 = 256;              // 2 x (16 hi + 16 lo)
@@ -128,7 +129,7 @@ predict_tc_kernel(const __grid_constant__ PredictLaunch pl, const DesignView d, 
       }
     }
   } else if (warp >= WARP_LOAD0) {
-    // =========================== gamma loaders (warps 4-7): one tcgen05.st pair per tile ===========================
+    // =========================== gamma loaders (warps 8-11): one tcgen05.st pair per tile ===========================
     const int r = threadIdx.x & 127;
     const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
     int lt = 0;
@@ -165,27 +166,31 @@ predict_tc_kernel(const __grid_constant__ PredictLaunch pl, const DesignView d, 
       if (lane == 0) mbar_arrive(bar_afull(ab));
     }
   } else {
-    // =========================== epilogue (warps 0-3): D -> + c -> swizzled tiles -> TMA store ===========================
-    const int r = threadIdx.x;
-    const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+    // =========================== epilogue groups (warps 0-3 / 4-7): D -> + c -> swizzled tiles -> TMA store ===========
+    // group g owns accumulator buffer g, staging buffer g and every chunk of the CTA's stream with parity g
+    const int grp = warp >> 2;
+    const int r = threadIdx.x & 127;
+    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const uint32_t row_off = static_cast<uint32_t>(r) * 128u;
     const uint32_t sw = static_cast<uint32_t>(r & 7);
-    int db = 0, ob = 0;
+    const uint32_t obase = s_out + grp * OUT_STAGE_BYTES;
+    const bool leader = (warp & 3) == 0;
     uint32_t dphase = 0;
+    int it = 0;                                            // position in the CTA's chunk stream
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t row = (int64_t)tile * TILE_M + r;
       const float c = (row < a.n) ? __ldg(a.out_c + row) : 0.f;
-      for (int ch = 0; ch < n_chunks; ++ch) {
-        mbar_wait(bar_dfull(db), dphase);
+      for (int ch = 0; ch < n_chunks; ++ch, ++it) {
+        if ((it & 1) != grp) continue;
+        mbar_wait(bar_dfull(grp), dphase);
+        dphase ^= 1u;
         tc_fence_after();
-        // the staging buffer `ob` was handed to TMA two chunks ago: its reads must be done before we overwrite it
-        if (warp == 0) bulk_wait_read1_elect();
-        named_bar_sync(1, 128);
-        const uint32_t obase = s_out + ob * OUT_STAGE_BYTES;
+        if (leader) bulk_wait_read_elect();                // this group's previous stores have read the staging tile
+        named_bar_sync(1 + grp, 128);
 #pragma unroll
         for (int j = 0; j < TN / 32; ++j) {
           uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_base + lane_addr + D_COL0 + db * TN + j * 32, v);
+          tmem_ld_32x32b_x32(tmem_base + lane_addr + D_COL0 + grp * TN + j * 32, v);
           tmem_wait_ld();
           const uint32_t rowp = obase + j * OUT_SUB_BYTES + row_off;
 #pragma unroll
@@ -197,20 +202,18 @@ predict_tc_kernel(const __grid_constant__ PredictLaunch pl, const DesignView d, 
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_dempty(db));       // accumulator buffer free for the MMA warp
+        if (lane == 0) mbar_arrive(bar_dempty(grp));      // accumulator buffer free for the MMA warp
         fence_proxy_async_smem();
-        named_bar_sync(1, 128);
-        if (warp == 0) {
+        named_bar_sync(1 + grp, 128);
+        if (leader) {
 #pragma unroll
           for (int j = 0; j < TN / 32; ++j)
             tma_store_2d_elect(pl.tmap_out, obase + j * OUT_SUB_BYTES, ch * TN + j * 32, tile * TILE_M);
           bulk_commit_elect();
         }
-        ob ^= 1;
-        if (++db == 2) { db = 0; dphase ^= 1u; }
       }
     }
-    if (warp == 0) bulk_wait_all_elect();
+    if (leader) bulk_wait_all_elect();
   }
 
   tc_fence_before();
