@@ -43,6 +43,7 @@ struct Smem {
 __global__ void __launch_bounds__(THREADS, 1)
 predict_tc_kernel(const __grid_constant__ PredictLaunch pl, const DesignView d, const FitArgs a, const int n_tiles,
                   const int n_chunks) {
+  const int64_t n_units = (int64_t)n_tiles * n_chunks;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   const uint32_t sbase = smem_u32(smem);
@@ -85,57 +86,58 @@ predict_tc_kernel(const __grid_constant__ PredictLaunch pl, const DesignView d, 
 
   if (warp == WARP_PROD) {
     // =========================== TMA producer: design rows of the prediction window ===========================
+    // Work units are (tile, chunk) pairs in chunk-major order, dealt round-robin to the CTAs: at any moment the
+    // CTAs with neighbouring ids write neighbouring 512-B pieces of the SAME 128 rows, i.e. one contiguous region
+    // of the table, instead of 148 unrelated row sets (DRAM write locality).
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      for (int ch = 0; ch < n_chunks; ++ch) {
-        mbar_wait(bar_bempty(stage), phase ^ 1u);
-        const int t0 = a.pred_start + ch * TN;
-        tma_load_2d_x2_elect(bar_bfull(stage), B_STAGE_BYTES,
-                             s_b + stage * B_STAGE_BYTES, pl.tmap_bhi, 0, t0, L2_EVICT_LAST,
-                             s_b + stage * B_STAGE_BYTES + B_TILE_BYTES, pl.tmap_blo, 0, t0, L2_EVICT_LAST);
-        if (++stage == SB) { stage = 0; phase ^= 1u; }
-      }
+    for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int ch = (int)(u % n_chunks);
+      mbar_wait(bar_bempty(stage), phase ^ 1u);
+      const int t0 = a.pred_start + ch * TN;
+      tma_load_2d_x2_elect(bar_bfull(stage), B_STAGE_BYTES,
+                           s_b + stage * B_STAGE_BYTES, pl.tmap_bhi, 0, t0, L2_EVICT_LAST,
+                           s_b + stage * B_STAGE_BYTES + B_TILE_BYTES, pl.tmap_blo, 0, t0, L2_EVICT_LAST);
+      if (++stage == SB) { stage = 0; phase ^= 1u; }
     }
   } else if (warp == WARP_MMA) {
     // =========================== MMA issuer ===========================
     constexpr uint32_t IDESC = umma_idesc_tf32(TILE_M, TN);
-    int stage = 0, db = 0, lt = 0;
-    uint32_t phase = 0, dphase = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
-      const int ab = lt & 1;
-      mbar_wait(bar_afull(ab), (lt >> 1) & 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    int64_t k = 0;                                         // this CTA's unit counter: A / D buffer = k & 1
+    for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++k) {
+      const int ab = (int)(k & 1);
+      const uint32_t par = (uint32_t)((k >> 1) & 1);
+      mbar_wait(bar_afull(ab), par);
+      mbar_wait(bar_bfull(stage), phase);
+      mbar_wait(bar_dempty(ab), par ^ 1u);
       tc_fence_after();
       const uint32_t a_hi = tmem_base + A_COL0 + ab * 32;
       const uint32_t a_lo = a_hi + 16;
-      for (int ch = 0; ch < n_chunks; ++ch) {
-        mbar_wait(bar_bfull(stage), phase);
-        mbar_wait(bar_dempty(db), dphase ^ 1u);
-        tc_fence_after();
-        const uint64_t bhi = umma_desc_k_sw64(s_b + stage * B_STAGE_BYTES);
-        const uint64_t blo = umma_desc_k_sw64(s_b + stage * B_STAGE_BYTES + B_TILE_BYTES);
-        const uint32_t dcol = tmem_base + D_COL0 + db * TN;
+      const uint64_t bhi = umma_desc_k_sw64(s_b + stage * B_STAGE_BYTES);
+      const uint64_t blo = umma_desc_k_sw64(s_b + stage * B_STAGE_BYTES + B_TILE_BYTES);
+      const uint32_t dcol = tmem_base + D_COL0 + ab * TN;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          umma_tf32_ts_elect(dcol, a_hi + k * 8, bhi + static_cast<uint64_t>(k * 2), IDESC, k ? 1u : 0u);
-          umma_tf32_ts_elect(dcol, a_hi + k * 8, blo + static_cast<uint64_t>(k * 2), IDESC, 1u);
-          umma_tf32_ts_elect(dcol, a_lo + k * 8, bhi + static_cast<uint64_t>(k * 2), IDESC, 1u);
-        }
-        umma_commit_elect(bar_bempty(stage));
-        umma_commit_elect(bar_dfull(db));
-        if (ch == n_chunks - 1) umma_commit_elect(bar_aempty(ab));
-        if (++stage == SB) { stage = 0; phase ^= 1u; }
-        if (++db == 2) { db = 0; dphase ^= 1u; }
+      for (int kk = 0; kk < 2; ++kk) {
+        umma_tf32_ts_elect(dcol, a_hi + kk * 8, bhi + static_cast<uint64_t>(kk * 2), IDESC, kk ? 1u : 0u);
+        umma_tf32_ts_elect(dcol, a_hi + kk * 8, blo + static_cast<uint64_t>(kk * 2), IDESC, 1u);
+        umma_tf32_ts_elect(dcol, a_lo + kk * 8, bhi + static_cast<uint64_t>(kk * 2), IDESC, 1u);
       }
+      umma_commit_elect(bar_bempty(stage));
+      umma_commit_elect(bar_dfull(ab));
+      umma_commit_elect(bar_aempty(ab));
+      if (++stage == SB) { stage = 0; phase ^= 1u; }
     }
   } else if (warp >= WARP_LOAD0) {
     // =========================== gamma loaders (warps 8-11): one tcgen05.st pair per tile ===========================
     const int r = threadIdx.x & 127;
     const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    int lt = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
-      const int ab = lt & 1;
-      const int64_t row = (int64_t)tile * TILE_M + r;
+    int64_t k = 0;
+    for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++k) {
+      const int ab = (int)(k & 1);
+      const int lt = (int)k;
+      const int64_t row = (u / n_chunks) * TILE_M + r;
       float g[P];
       if (row < a.n) {
         const float4* gp = reinterpret_cast<const float4*>(a.out_gamma + row * P);
@@ -175,42 +177,39 @@ predict_tc_kernel(const __grid_constant__ PredictLaunch pl, const DesignView d, 
     const uint32_t sw = static_cast<uint32_t>(r & 7);
     const uint32_t obase = s_out + grp * OUT_STAGE_BYTES;
     const bool leader = (warp & 3) == 0;
-    uint32_t dphase = 0;
-    int it = 0;                                            // position in the CTA's chunk stream
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    int64_t k = 0;                                         // unit counter: group g owns the units with k & 1 == g
+    for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++k) {
+      if ((int)(k & 1) != grp) continue;
+      const int tile = (int)(u / n_chunks), ch = (int)(u % n_chunks);
       const int64_t row = (int64_t)tile * TILE_M + r;
       const float c = (row < a.n) ? __ldg(a.out_c + row) : 0.f;
-      for (int ch = 0; ch < n_chunks; ++ch, ++it) {
-        if ((it & 1) != grp) continue;
-        mbar_wait(bar_dfull(grp), dphase);
-        dphase ^= 1u;
-        tc_fence_after();
-        if (leader) bulk_wait_read_elect();                // this group's previous stores have read the staging tile
-        named_bar_sync(1 + grp, 128);
+      mbar_wait(bar_dfull(grp), (uint32_t)((k >> 1) & 1));
+      tc_fence_after();
+      if (leader) bulk_wait_read_elect();                  // this group's previous stores have read the staging tile
+      named_bar_sync(1 + grp, 128);
 #pragma unroll
-        for (int j = 0; j < TN / 32; ++j) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_base + lane_addr + D_COL0 + grp * TN + j * 32, v);
-          tmem_wait_ld();
-          const uint32_t rowp = obase + j * OUT_SUB_BYTES + row_off;
+      for (int j = 0; j < TN / 32; ++j) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_addr + D_COL0 + grp * TN + j * 32, v);
+        tmem_wait_ld();
+        const uint32_t rowp = obase + j * OUT_SUB_BYTES + row_off;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 o = make_float4(__uint_as_float(v[4 * q]) + c, __uint_as_float(v[4 * q + 1]) + c,
-                                         __uint_as_float(v[4 * q + 2]) + c, __uint_as_float(v[4 * q + 3]) + c);
-            sts128(rowp + ((static_cast<uint32_t>(q) ^ sw) << 4), o);
-          }
+        for (int q = 0; q < 8; ++q) {
+          const float4 o = make_float4(__uint_as_float(v[4 * q]) + c, __uint_as_float(v[4 * q + 1]) + c,
+                                       __uint_as_float(v[4 * q + 2]) + c, __uint_as_float(v[4 * q + 3]) + c);
+          sts128(rowp + ((static_cast<uint32_t>(q) ^ sw) << 4), o);
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_dempty(grp));      // accumulator buffer free for the MMA warp
-        fence_proxy_async_smem();
-        named_bar_sync(1 + grp, 128);
-        if (leader) {
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_dempty(grp));        // accumulator buffer free for the MMA warp
+      fence_proxy_async_smem();
+      named_bar_sync(1 + grp, 128);
+      if (leader) {
 #pragma unroll
-          for (int j = 0; j < TN / 32; ++j)
-            tma_store_2d_elect(pl.tmap_out, obase + j * OUT_SUB_BYTES, ch * TN + j * 32, tile * TILE_M);
-          bulk_commit_elect();
-        }
+        for (int j = 0; j < TN / 32; ++j)
+          tma_store_2d_elect(pl.tmap_out, obase + j * OUT_SUB_BYTES, ch * TN + j * 32, tile * TILE_M);
+        bulk_commit_elect();
       }
     }
     if (leader) bulk_wait_all_elect();
@@ -234,7 +233,8 @@ cudaError_t launch_predict_tc(const DesignView& d, const FitArgs& a, const Predi
   const size_t smem = Smem::total + 1024;
   cudaError_t e = cudaFuncSetAttribute(predict_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const int grid = n_tiles < sm_count ? n_tiles : sm_count;
+  const int64_t n_units = (int64_t)n_tiles * n_chunks;
+  const int grid = n_units < sm_count ? (int)n_units : sm_count;
   predict_tc_kernel<<<grid, THREADS, smem, s>>>(pl, d, a, n_tiles, n_chunks);
   return cudaGetLastError();
 }
