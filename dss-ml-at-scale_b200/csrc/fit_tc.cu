@@ -59,7 +59,7 @@ struct SmemLayout {
   static constexpr int ostage = apred + MAX_PRED * P * 4;            // forecast tile staged for the bulk stores
   static constexpr int nm = ostage + TILE_M * BULK_MAX_PRED * 4;     // per-row missing counts: [NM_RING][2 groups][128] u16
   static constexpr int bars = nm + NM_RING * NGROUPS * TILE_M * 2;
-  static constexpr int n_bars = 2 * STAGES + 2 * NGROUPS * ASLOTS + 4;
+  static constexpr int n_bars = 2 * STAGES + 2 * NGROUPS * ASLOTS + 4 + NM_RING;
   static constexpr int tmem_ptr = bars + n_bars * 8;
   static constexpr int total = tmem_ptr + 16;
 };
@@ -117,6 +117,7 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
   auto bar_aempty = [&](int g, int j) { return s_bars + 8u * (2 * STAGES + NGROUPS * ASLOTS + g * ASLOTS + j); };
   auto bar_accfull = [&](int b) { return s_bars + 8u * (2 * STAGES + 2 * NGROUPS * ASLOTS + b); };
   auto bar_accempty = [&](int b) { return s_bars + 8u * (2 * STAGES + 2 * NGROUPS * ASLOTS + 2 + b); };
+  auto bar_nm = [&](int i) { return s_bars + 8u * (2 * STAGES + 2 * NGROUPS * ASLOTS + 4 + i); };   // s_nm slot published
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + SmemLayout::tmem_ptr);
 
   const int warp = threadIdx.x >> 5;
@@ -139,6 +140,8 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
         mbar_init(bar_accfull(b), 1);     // tcgen05.commit after the tile's last chunk
         mbar_init(bar_accempty(b), 4);    // 4 epilogue warps have read the accumulators
       }
+      // gap counts of a tile: one arrival per transform warp that owns a chunk of it (release) -> epilogue (acquire)
+      for (int i = 0; i < NM_RING; ++i) mbar_init(bar_nm(i), n_chunks >= 2 ? 8 : 4);
       fence_mbar_init();
     }
     __syncwarp();
@@ -294,7 +297,8 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
       const uint32_t a_hi = tmem_base + lane_addr + ASLOT_COL0 + (grp * ASLOTS + aslot) * 64;
       tmem_st_32x32b_x32(a_hi, hi);
       tmem_st_32x32b_x32(a_hi + 32, lo);
-      if (collect && ch + NGROUPS >= n_chunks) {        // my last chunk of this tile: publish the count (the arrive releases it)
+      const bool last_own = collect && ch + NGROUPS >= n_chunks;       // my last chunk of this tile
+      if (last_own) {
         const int cnt = nm > 0x7ffe ? 0x7ffe : nm;
         s_nm[((lt & (NM_RING - 1)) * NGROUPS + grp) * TILE_M + r] = static_cast<uint16_t>(cnt | (bad ? 0x8000 : 0));
       }
@@ -304,6 +308,7 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
       if (lane == 0) {
         mbar_arrive(bar_afull(grp, aslot));
         mbar_arrive(bar_empty(stage));                  // this warp's smem reads of the stage are done
+        if (last_own) mbar_arrive(bar_nm(lt & (NM_RING - 1)));     // releases this warp's s_nm entries to the epilogue
       }
       stage += NGROUPS;
       if (stage >= STAGES) { stage -= STAGES; phase ^= 1u; }
@@ -349,6 +354,7 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
       int nm0 = 0, nm1 = 0;
       bool general = false;
       if (collect) {
+        mbar_wait(bar_nm(lt & (NM_RING - 1)), (lt / NM_RING) & 1);     // acquire the transform warps' counts
         const uint16_t* nmrow = s_nm + (lt & (NM_RING - 1)) * NGROUPS * TILE_M + r;
         const bool has0 = n_chunks >= 2 || ((lt * n_chunks) & 1) == 0;
         const bool has1 = n_chunks >= 2 || ((lt * n_chunks) & 1) == 1;

@@ -332,6 +332,7 @@ fit_warp_kernel(const DesignView d, const FitArgs a, const int smem_rows) {
       miss[s] = __reduce_add_sync(0xffffffffu, miss[s]);
     }
 
+    __syncwarp();                                    // missing positions recorded by other lanes are visible now
     // ---- series with gaps: per-series normal equations (rare path, one copy of the code)
     int st[S];
     bool deferred[S];
