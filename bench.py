@@ -323,11 +323,28 @@ def run_ours(args):
         del ref, loc
 
     # ---- roofline of the dominant kernel (algorithmic bytes: 4*T read + 4*H written per series)
+    def ncu_traffic():
+        """dram__bytes_read.sum + dram__bytes_write.sum per launch of fit_tc_kernel from the committed
+        `ncu --set full` capture (profiles/r01/final_tc_final.txt) -- valid for the workload it was taken on."""
+        if not (kernel_used == "tc" and n == 1_000_000 and t == 1095 and h == 28 and args.mode == "future"
+                and args.nan_frac == 0.0):
+            return None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01", "final_tc_final.txt")) as f:
+                for line in f:
+                    if line.startswith("traffic (dram read + write) per launch:"):
+                        return float(line.split(":")[1].split()[0]) * 1e9
+        except OSError:
+            pass
+        return None
+
     peak, peak_src = peaks()
     bytes_per_series = 4 * t + 4 * h if args.mode == "future" else 4 * (t - h) + 4 * t
     achieved = n * bytes_per_series / (kern_ms_avg * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "fit_tc_kernel" if kernel_used == "tc" else "fit_warp_kernel",
+                "traffic": ncu_traffic(), "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01/final_tc_final.txt)",
+                "algorithmic_bytes_per_launch": n * bytes_per_series,
+                "kernel": "fit_tc_kernel" if kernel_used == "tc" else "fit_warp_kernel",
                 "peak_source": peak_src, "bytes_per_series": bytes_per_series,
                 "kernel_ms": kern_ms_avg,
                 "note": "CUDA events around each step's libmmf launches in the timed region, max over ranks"}
