@@ -21,7 +21,7 @@ EXPORTS = (
     "mmf_version", "mmf_last_error", "mmf_device_count", "mmf_create", "mmf_destroy",
     "mmf_set_stream", "mmf_synchronize", "mmf_plan_design", "mmf_get_whitening",
     "mmf_fit_forecast_f32", "mmf_fit_forecast_bcast_f32", "mmf_fit_select_forecast_f32", "mmf_pack_hash_utf8", "mmf_pack_hash_i32",
-    "mmf_pack_group_codes", "mmf_pack_minmax", "mmf_pack_scatter_f32", "mmf_alloc_pinned", "mmf_free_pinned",
+    "mmf_pack_group_codes", "mmf_pack_verify_utf8", "mmf_pack_verify_i32", "mmf_pack_minmax", "mmf_pack_scatter_f32", "mmf_alloc_pinned", "mmf_free_pinned",
     "mmf_host_register", "mmf_host_unregister",
 )
 
@@ -94,6 +94,8 @@ def load() -> C.CDLL:
     lib.mmf_pack_hash_utf8.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]
     lib.mmf_pack_hash_i32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]
     lib.mmf_pack_group_codes.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
+    lib.mmf_pack_verify_utf8.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.mmf_pack_verify_i32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.mmf_pack_minmax.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
     lib.mmf_pack_scatter_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                          C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int32]

@@ -711,6 +711,22 @@ int mmf_pack_group_codes(mmf_ctx* ctx, const uint64_t* hash, int64_t n, int32_t*
   return MMF_OK;
 }
 
+int mmf_pack_verify_utf8(mmf_ctx* ctx, const int32_t* offsets, const uint8_t* data, int64_t n, const int32_t* gid,
+                         const int32_t* first_row, uint64_t* mismatches) {
+  PACK_PROLOGUE();
+  if (!mismatches) return fail(MMF_E_INVALID, "mismatches is NULL");
+  CU_TRY(pack_verify_utf8(offsets, data, n, gid, first_row, mismatches, ctx->sm_count, ctx->stream));
+  return MMF_OK;
+}
+
+int mmf_pack_verify_i32(mmf_ctx* ctx, const int32_t* values, int64_t n, const int32_t* gid, const int32_t* first_row,
+                        uint64_t* mismatches) {
+  PACK_PROLOGUE();
+  if (!mismatches) return fail(MMF_E_INVALID, "mismatches is NULL");
+  CU_TRY(pack_verify_i32(values, n, gid, first_row, mismatches, ctx->sm_count, ctx->stream));
+  return MMF_OK;
+}
+
 int mmf_pack_minmax(mmf_ctx* ctx, const int32_t* gid, const int32_t* day, int64_t n, int32_t n_groups,
                     int32_t* gmin, int32_t* gmax) {
   PACK_PROLOGUE();

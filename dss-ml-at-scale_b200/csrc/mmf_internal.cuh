@@ -111,6 +111,10 @@ cudaError_t launch_select(const DesignView& d, const FitArgs& a, const SelectArg
 cudaError_t pack_hash_utf8(const int32_t* offsets, const uint8_t* data, int64_t n, uint64_t* h, int first, int sm,
                            cudaStream_t s);
 cudaError_t pack_hash_i32(const int32_t* v, int64_t n, uint64_t* h, int first, int sm, cudaStream_t s);
+cudaError_t pack_verify_utf8(const int32_t* offsets, const uint8_t* data, int64_t n, const int32_t* gid,
+                             const int32_t* first_row, uint64_t* mismatches, int sm, cudaStream_t s);
+cudaError_t pack_verify_i32(const int32_t* v, int64_t n, const int32_t* gid, const int32_t* first_row,
+                            uint64_t* mismatches, int sm, cudaStream_t s);
 cudaError_t pack_group_codes(const uint64_t* h, int64_t n, int32_t* gid, int32_t* first_row, int32_t* n_groups_host,
                              int sm, cudaStream_t s);
 cudaError_t pack_minmax(const int32_t* gid, const int32_t* day, int64_t n, int32_t n_groups, int32_t* gmin,

@@ -22,10 +22,16 @@ constexpr int TPB = 256;
 
 __device__ __forceinline__ uint64_t fnv1a_byte(uint64_t h, uint32_t b) { return (h ^ b) * 1099511628211ull; }
 
+// first == 1: the standard FNV offset basis; first > 1: a different basis per value, for the re-hash after a
+// detected collision (verify_* below)
+__device__ __forceinline__ uint64_t fnv_basis(int first) {
+  return 14695981039346656037ull ^ ((uint64_t)(first - 1) * 0x9E3779B97F4A7C15ull);
+}
+
 __global__ void hash_utf8_kernel(const int32_t* __restrict__ offsets, const uint8_t* __restrict__ data, int64_t n,
                                  uint64_t* __restrict__ h, int first) {
   for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += (int64_t)gridDim.x * TPB) {
-    uint64_t x = first ? 14695981039346656037ull : h[i];
+    uint64_t x = first ? fnv_basis(first) : h[i];
     const int32_t lo = offsets[i], hi = offsets[i + 1];
     for (int32_t k = lo; k < hi; ++k) x = fnv1a_byte(x, data[k]);
     x = fnv1a_byte(x, 0xffu);                       // column separator: ("ab","c") != ("a","bc")
@@ -35,7 +41,7 @@ __global__ void hash_utf8_kernel(const int32_t* __restrict__ offsets, const uint
 
 __global__ void hash_i32_kernel(const int32_t* __restrict__ v, int64_t n, uint64_t* __restrict__ h, int first) {
   for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += (int64_t)gridDim.x * TPB) {
-    uint64_t x = first ? 14695981039346656037ull : h[i];
+    uint64_t x = first ? fnv_basis(first) : h[i];
     const uint32_t u = static_cast<uint32_t>(v[i]);
     x = fnv1a_byte(x, u & 0xffu); x = fnv1a_byte(x, (u >> 8) & 0xffu);
     x = fnv1a_byte(x, (u >> 16) & 0xffu); x = fnv1a_byte(x, u >> 24);
@@ -62,6 +68,27 @@ __global__ void codes_kernel(const int32_t* __restrict__ scan, const int32_t* __
     gid[sorted_row[i]] = g;
     if (head[i]) first_row[g] = sorted_row[i];
   }
+}
+
+// rows grouped by hash only: check every row's key against the key of its group's first row (a 64-bit collision
+// would silently merge two series).  One coalesced pass over the key column + a gather of the group head's key.
+__global__ void verify_utf8_kernel(const int32_t* __restrict__ offsets, const uint8_t* __restrict__ data, int64_t n,
+                                   const int32_t* __restrict__ gid, const int32_t* __restrict__ first_row,
+                                   unsigned long long* __restrict__ mismatches) {
+  for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += (int64_t)gridDim.x * TPB) {
+    const int32_t j = first_row[gid[i]];
+    if (j == i) continue;
+    const int32_t lo = offsets[i], len = offsets[i + 1] - lo, lo2 = offsets[j];
+    bool same = (offsets[j + 1] - lo2) == len;
+    for (int32_t k = 0; same && k < len; ++k) same = data[lo + k] == data[lo2 + k];
+    if (!same) atomicAdd(mismatches, 1ull);
+  }
+}
+
+__global__ void verify_i32_kernel(const int32_t* __restrict__ v, int64_t n, const int32_t* __restrict__ gid,
+                                  const int32_t* __restrict__ first_row, unsigned long long* __restrict__ mismatches) {
+  for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += (int64_t)gridDim.x * TPB)
+    if (v[i] != v[first_row[gid[i]]]) atomicAdd(mismatches, 1ull);
 }
 
 __global__ void minmax_kernel(const int32_t* __restrict__ gid, const int32_t* __restrict__ day, int64_t n,
@@ -119,6 +146,19 @@ cudaError_t pack_hash_utf8(const int32_t* offsets, const uint8_t* data, int64_t 
 }
 cudaError_t pack_hash_i32(const int32_t* v, int64_t n, uint64_t* h, int first, int sm, cudaStream_t s) {
   if (n > 0) hash_i32_kernel<<<grid_for(n, sm), TPB, 0, s>>>(v, n, h, first);
+  return cudaGetLastError();
+}
+
+cudaError_t pack_verify_utf8(const int32_t* offsets, const uint8_t* data, int64_t n, const int32_t* gid,
+                             const int32_t* first_row, uint64_t* mismatches, int sm, cudaStream_t s) {
+  if (n > 0) verify_utf8_kernel<<<grid_for(n, sm), TPB, 0, s>>>(offsets, data, n, gid, first_row,
+                                                                reinterpret_cast<unsigned long long*>(mismatches));
+  return cudaGetLastError();
+}
+cudaError_t pack_verify_i32(const int32_t* v, int64_t n, const int32_t* gid, const int32_t* first_row,
+                            uint64_t* mismatches, int sm, cudaStream_t s) {
+  if (n > 0) verify_i32_kernel<<<grid_for(n, sm), TPB, 0, s>>>(v, n, gid, first_row,
+                                                               reinterpret_cast<unsigned long long*>(mismatches));
   return cudaGetLastError();
 }
 

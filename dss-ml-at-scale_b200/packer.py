@@ -6,7 +6,7 @@ The reference gets each group's rows together with a Spark hash shuffle
 re-indexes on the regular grid (``sort_values("Date")``, ``set_index("Date").asfreq(freq)``,
 02:422-423).  Here the Arrow column buffers of the whole table go to the GPU unchanged and
 four small kernels of ``libmmf.so`` (csrc/pack.cu) do the same for all groups at once:
-64-bit hash of the key columns -> dense group codes (radix sort) -> per-group first/last day
+64-bit hash of the key columns -> dense group codes (radix sort), checked against the key bytes -> per-group first/last day
 -> scatter into NaN-filled rows.  Only G-sized metadata (first/last day and one key row per
 group) ever comes back to the host.
 
@@ -34,27 +34,20 @@ def _dev_from_numpy(a: np.ndarray, device):
         return torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=False)
 
 
-def _hash_keys(lib, h, table, keys, n, device):
-    """Chain every key column into the per-row 64-bit hash (device)."""
+def _stage_keys(table, keys, n, device):
+    """Key columns -> device buffers, as Arrow holds them: ("i32", values) or ("utf8", offsets, bytes)."""
     import pyarrow as pa
     import pyarrow.compute as pc
-    import torch
 
-    hash_dev = torch.empty(n, dtype=torch.int64, device=device)      # bit container for uint64
-    first = 1
-    keep = []                                                          # keep device buffers alive until the sync
+    staged = []
     for k in keys:
         col = table.column(k)
         col = col.combine_chunks() if isinstance(col, pa.ChunkedArray) else col
         if pa.types.is_dictionary(col.type):
             idx = col.indices.cast(pa.int32()).to_numpy(zero_copy_only=False)
-            d_idx = _dev_from_numpy(idx.astype(np.int32, copy=False), device)
-            keep.append(d_idx)
-            N.check(lib.mmf_pack_hash_i32(h, d_idx.data_ptr(), n, hash_dev.data_ptr(), first))
+            staged.append(("i32", _dev_from_numpy(idx.astype(np.int32, copy=False), device)))
         elif pa.types.is_integer(col.type):
-            d_idx = _dev_from_numpy(pc.cast(col, pa.int32()).to_numpy(zero_copy_only=False), device)
-            keep.append(d_idx)
-            N.check(lib.mmf_pack_hash_i32(h, d_idx.data_ptr(), n, hash_dev.data_ptr(), first))
+            staged.append(("i32", _dev_from_numpy(pc.cast(col, pa.int32()).to_numpy(zero_copy_only=False), device)))
         else:
             if pa.types.is_large_string(col.type):
                 col = col.cast(pa.string())
@@ -63,11 +56,54 @@ def _hash_keys(lib, h, table, keys, n, device):
             bufs = col.buffers()
             offsets = np.frombuffer(bufs[1], dtype=np.int32)[col.offset:col.offset + n + 1]
             data = np.frombuffer(bufs[2], dtype=np.uint8) if bufs[2] is not None and bufs[2].size else np.zeros(1, np.uint8)
-            d_off, d_dat = _dev_from_numpy(offsets, device), _dev_from_numpy(data, device)
-            keep += [d_off, d_dat]
-            N.check(lib.mmf_pack_hash_utf8(h, d_off.data_ptr(), d_dat.data_ptr(), n, hash_dev.data_ptr(), first))
+            staged.append(("utf8", _dev_from_numpy(offsets, device), _dev_from_numpy(data, device)))
+    return staged
+
+
+def _hash_keys(lib, h, staged, n, device, seed: int = 1):
+    """Chain every key column into the per-row 64-bit hash (device).  ``seed`` >= 1 picks the FNV basis."""
+    import torch
+
+    hash_dev = torch.empty(n, dtype=torch.int64, device=device)      # bit container for uint64
+    first = seed
+    for col in staged:
+        if col[0] == "i32":
+            N.check(lib.mmf_pack_hash_i32(h, col[1].data_ptr(), n, hash_dev.data_ptr(), first))
+        else:
+            N.check(lib.mmf_pack_hash_utf8(h, col[1].data_ptr(), col[2].data_ptr(), n, hash_dev.data_ptr(), first))
         first = 0
-    return hash_dev, keep
+    return hash_dev
+
+
+def _count_collisions(lib, h, staged, n, gid, first_row, device) -> int:
+    """Rows whose key differs from the key of their group's first row (two keys sharing one 64-bit hash)."""
+    import torch
+
+    bad = torch.zeros(1, dtype=torch.int64, device=device)
+    for col in staged:
+        if col[0] == "i32":
+            N.check(lib.mmf_pack_verify_i32(h, col[1].data_ptr(), n, gid.data_ptr(), first_row.data_ptr(), bad.data_ptr()))
+        else:
+            N.check(lib.mmf_pack_verify_utf8(h, col[1].data_ptr(), col[2].data_ptr(), n, gid.data_ptr(),
+                                             first_row.data_ptr(), bad.data_ptr()))
+    return int(bad.item())
+
+
+def group_rows_device(lib, h, staged, n, device, max_rehash: int = 3):
+    """(gid[n], first_row[>=G], G): dense group code per row, verified against the key bytes; a detected hash
+    collision re-hashes with another basis (and raises after ``max_rehash`` tries, never merges groups silently)."""
+    import torch
+
+    for seed in range(1, max_rehash + 1):
+        hash_dev = _hash_keys(lib, h, staged, n, device, seed)
+        gid = torch.empty(n, dtype=torch.int32, device=device)
+        first_row = torch.empty(n, dtype=torch.int32, device=device)
+        g_host = C.c_int32(0)
+        N.check(lib.mmf_pack_group_codes(h, hash_dev.data_ptr(), n, gid.data_ptr(), first_row.data_ptr(), C.byref(g_host)))
+        del hash_dev
+        if _count_collisions(lib, h, staged, n, gid, first_row, device) == 0:
+            return gid, first_row, int(g_host.value)
+    raise RuntimeError(f"key hash collisions persisted over {max_rehash} hash bases")
 
 
 def pack_table_device(table, keys=("Product", "SKU"), date_col="Date", value_col="Demand", freq="W-MON",
@@ -101,13 +137,9 @@ def pack_table_device(table, keys=("Product", "SKU"), date_col="Date", value_col
     val = _dev_from_numpy(pc.cast(table.column(value_col).combine_chunks(), pa.float32())
                           .to_numpy(zero_copy_only=False).astype(np.float32, copy=False), device)
 
-    hash_dev, keep = _hash_keys(lib, h, table, keys, n, device)
-    gid = torch.empty(n, dtype=torch.int32, device=device)
-    first_row = torch.empty(n, dtype=torch.int32, device=device)
-    g_host = C.c_int32(0)
-    N.check(lib.mmf_pack_group_codes(h, hash_dev.data_ptr(), n, gid.data_ptr(), first_row.data_ptr(), C.byref(g_host)))
-    G = int(g_host.value)
-    del keep, hash_dev
+    staged = _stage_keys(table, keys, n, device)
+    gid, first_row, G = group_rows_device(lib, h, staged, n, device)
+    del staged
     gmin = torch.empty(G, dtype=torch.int32, device=device)
     gmax = torch.empty(G, dtype=torch.int32, device=device)
     N.check(lib.mmf_pack_minmax(h, gid.data_ptr(), day.data_ptr(), n, G, gmin.data_ptr(), gmax.data_ptr()))

@@ -136,3 +136,29 @@ class SymmetricTable:
     def fit_into(self, engine, y_local, pred_start: int, n_pred: int, status=None):
         """Fit this rank's rows and broadcast their forecasts into every rank's table copy."""
         engine.fit_forecast_bcast(y_local, pred_start, n_pred, self.out_ptrs, self.n_pred, self.multimem, status=status)
+
+
+def forecast_groups_sharded(pdf, *, keys=("Product", "SKU"), group=None, gather: bool = True, engine=None, **kw):
+    """DataFrame-level analogue of the reference's distributed fan-out (02:520-528), one process per GPU:
+    ``owner = hash(key) mod world`` (the ``repartition(n_tasks, "Product", "SKU")`` shuffle), every rank runs
+    ``forecast_groups`` on the groups it owns -- no communication during the fit -- and, with ``gather=True``,
+    every rank ends up with the whole ``tuning_schema`` frame (groups in key order).  ``pdf`` must hold all rows
+    of the groups this rank owns (e.g. the same frame on every rank, or a frame pre-partitioned by the same hash).
+    For packed data use ``ShardPlan`` + ``forecast_packed_sharded`` / ``SymmetricTable`` (numeric table only)."""
+    import pandas as pd
+    import torch.distributed as dist
+
+    from .frames import forecast_groups
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    keys = list(keys)
+    owner = owner_of_keys(pdf[keys], world) if len(pdf) else np.zeros(0, dtype=np.int64)
+    local = forecast_groups(pdf[owner == rank], keys=keys, engine=engine, **kw)
+    if not gather or world == 1:
+        return local
+    parts = [None] * world
+    dist.all_gather_object(parts, local, group=group)
+    out = pd.concat([p for p in parts if len(p)], ignore_index=True) if any(len(p) for p in parts) else local
+    date_col = kw.get("date_col", "Date")
+    return out.sort_values(keys + [date_col], kind="stable", ignore_index=True)

@@ -148,9 +148,12 @@ int mmf_fit_select_forecast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t
  * sort_values("Date") + set_index("Date").asfreq(freq) (02:422-423).  All pointers are DEVICE pointers holding
  * the Arrow column buffers as they are; rows may arrive in any order.
  *   hash_utf8 / hash_i32 : chain a utf8 (offsets+bytes) or dictionary-index key column into a 64-bit FNV-1a row
- *                          hash (first != 0 starts a new hash, 0 continues `hash`)
+ *                          hash (first != 0 starts a new hash, 0 continues `hash`; first = 1 is the standard
+ *                          FNV basis, first = 2, 3, ... other bases for a re-hash after a collision)
  *   group_codes          : dense group code per row (groups numbered in hash order), the first row of every
  *                          group (to read its key values back) and the number of groups (host int, synchronises)
+ *   verify_utf8 / _i32   : adds to *mismatches (device uint64, caller zeroes it) the rows whose key differs from
+ *                          the key of their group's first row, i.e. rows merged by a 64-bit hash collision
  *   minmax               : first / last day of every group
  *   scatter_f32          : y[row_of_group[g], (day - gstart[g]) / step] = value after a NaN fill; rows of groups with
  *                          row_of_group < 0 (other calendar buckets) and off-grid dates are skipped            */
@@ -159,6 +162,10 @@ int mmf_pack_hash_utf8(mmf_ctx* ctx, const int32_t* offsets, const uint8_t* data
 int mmf_pack_hash_i32(mmf_ctx* ctx, const int32_t* values, int64_t n, uint64_t* hash, int32_t first);
 int mmf_pack_group_codes(mmf_ctx* ctx, const uint64_t* hash, int64_t n, int32_t* gid, int32_t* first_row,
                          int32_t* n_groups);
+int mmf_pack_verify_utf8(mmf_ctx* ctx, const int32_t* offsets, const uint8_t* data, int64_t n, const int32_t* gid,
+                         const int32_t* first_row, uint64_t* mismatches);
+int mmf_pack_verify_i32(mmf_ctx* ctx, const int32_t* values, int64_t n, const int32_t* gid, const int32_t* first_row,
+                        uint64_t* mismatches);
 int mmf_pack_minmax(mmf_ctx* ctx, const int32_t* gid, const int32_t* day, int64_t n, int32_t n_groups,
                     int32_t* gmin, int32_t* gmax);
 int mmf_pack_scatter_f32(mmf_ctx* ctx, const int32_t* gid, const int32_t* day, const float* val, int64_t n,

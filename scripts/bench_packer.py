@@ -37,11 +37,14 @@ def main():
     gid = torch.empty(n, dtype=torch.int32, device="cuda")
     first = torch.empty(n, dtype=torch.int32, device="cuda")
     out = torch.empty((G, (T + 3) & ~3), device="cuda")
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda")
 
     def device_pass():
         g = C.c_int32(0)
         N.check(lib.mmf_pack_hash_i32(h, item.data_ptr(), n, hsh.data_ptr(), 1))
         N.check(lib.mmf_pack_group_codes(h, hsh.data_ptr(), n, gid.data_ptr(), first.data_ptr(), C.byref(g)))
+        bad.zero_()
+        N.check(lib.mmf_pack_verify_i32(h, item.data_ptr(), n, gid.data_ptr(), first.data_ptr(), bad.data_ptr()))
         gmin = torch.empty(g.value, dtype=torch.int32, device="cuda")
         gmax = torch.empty(g.value, dtype=torch.int32, device="cuda")
         N.check(lib.mmf_pack_minmax(h, gid.data_ptr(), day.data_ptr(), n, g.value, gmin.data_ptr(), gmax.data_ptr()))

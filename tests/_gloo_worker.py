@@ -18,11 +18,22 @@ from oracle import mmf_oracle as O  # noqa: E402
 class OracleEngine:
     """Stands in for ForecastEngine on the CPU box (test infrastructure only)."""
 
-    def __init__(self, X, t_fit):
+    def __init__(self, X=None, t_fit=None):
         self.X, self.t_fit = X, t_fit
+
+    def plan_calendar(self, start, t_len, freq="D", horizon=28, mode="future", design="trend_season_exog"):
+        if mode == "holdout":
+            self.t_fit, n_rows, ps, npred = t_len - horizon, t_len, 0, t_len
+        else:
+            self.t_fit, n_rows, ps, npred = t_len, t_len + horizon, t_len, horizon
+        days = mmf.design.calendar_grid(start, n_rows, freq)
+        self.X = mmf.design.design_matrix(days, self.t_fit, design)
+        return days[ps:ps + npred], ps, npred
 
     def fit_forecast(self, y, pred_start, n_pred, out=None):
         pred, _ = O.fit_forecast_packed(y, self.X, self.t_fit, pred_start, n_pred)
+        if out is None:
+            return pred.astype(np.float32)
         out[...] = pred.astype(np.float32)
         return out
 
@@ -47,6 +58,15 @@ def main():
     full[rank * plan2.per: rank * plan2.per + lo.size] = torch.from_numpy(want[lo].astype(np.float32))
     SH.all_gather_inplace(full, plan2)
     assert np.allclose(full[torch.as_tensor(plan2.gather_index())].numpy(), want.astype(np.float32))
+    # DataFrame level: hash-shard the groups of a long frame, fit locally, gather the whole tuning_schema frame
+    df = mmf.synth.reference_weekly_demand(n_skus=2)
+    got = SH.forecast_groups_sharded(df, engine=OracleEngine())
+    ref = mmf.forecast_groups(df, engine=OracleEngine())
+    assert list(got.columns) == ["Product", "SKU", "Date", "Demand", "Demand_Fitted"] and len(got) == len(ref) == 10 * 157
+    assert (got["SKU"].to_numpy() == ref["SKU"].to_numpy()).all()
+    assert np.array_equal(got["Demand_Fitted"].to_numpy(), ref["Demand_Fitted"].to_numpy())
+    mine = SH.forecast_groups_sharded(df, engine=OracleEngine(), gather=False)
+    assert 0 < len(mine) < len(ref) and len(mine) % 157 == 0
     print(f"GLOO_OK rank {rank}", flush=True)
     dist.destroy_process_group()
 

@@ -390,6 +390,46 @@ def test_device_packer_large_daily():
     assert np.array_equal(got.cpu().numpy(), y)
 
 
+def test_packer_detects_hash_collisions_and_rehashes():
+    """Grouping is by 64-bit hash; verify_* compares every row's key with its group head's key.  A merged pair of
+    groups (what a collision would produce) is counted; a different hash basis regroups the same keys identically."""
+    import ctypes as C
+    import pyarrow as pa
+    import torch
+    from mmf import _native as N
+    from mmf import packer as PK
+    df = _long_frame(7)
+    table = pa.Table.from_pandas(df, preserve_index=False)
+    eng = mmf.default_engine()
+    lib, h = eng._lib, eng._h
+    dev = torch.device("cuda", torch.cuda.current_device())
+    eng.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    n = table.num_rows
+    for keys in (["Product", "SKU"], ["SKU"]):
+        staged = PK._stage_keys(table, keys, n, dev)
+        gid, first_row, G = PK.group_rows_device(lib, h, staged, n, dev)
+        assert G == df.groupby(keys).ngroups
+        assert PK._count_collisions(lib, h, staged, n, gid, first_row, dev) == 0
+        # same partition of the rows under another hash basis (codes are numbered in hash order, so compare via heads)
+        h2 = PK._hash_keys(lib, h, staged, n, dev, seed=2)
+        gid2 = torch.empty_like(gid); fr2 = torch.empty_like(first_row); g2 = C.c_int32(0)
+        N.check(lib.mmf_pack_group_codes(h, h2.data_ptr(), n, gid2.data_ptr(), fr2.data_ptr(), C.byref(g2)))
+        assert g2.value == G and not torch.equal(h2, PK._hash_keys(lib, h, staged, n, dev, seed=1))
+        pair = torch.stack([gid.long(), gid2.long()], 1).unique(dim=0)
+        assert pair.shape[0] == G                                     # a bijection between the two codings
+        # fake a collision: fold group 1 into group 0
+        merged = torch.where(gid == 1, torch.zeros_like(gid), gid)
+        bad = PK._count_collisions(lib, h, staged, n, merged, first_row, dev)
+        assert bad in (int((gid == 1).sum()) * k for k in range(1, len(keys) + 1))
+    # integer / dictionary keys go through verify_i32
+    t2 = table.set_column(1, "SKU", pa.array(df["SKU"]).dictionary_encode())
+    staged = PK._stage_keys(t2, ["Product", "SKU"], n, dev)
+    gid, first_row, G = PK.group_rows_device(lib, h, staged, n, dev)
+    merged = torch.where(gid == 2, torch.ones_like(gid), gid)
+    c = int((gid == 2).sum())                                         # counted once per differing key column
+    assert PK._count_collisions(lib, h, staged, n, merged, first_row, dev) in (c, 2 * c)
+
+
 # ---- on-device model selection (SURVEY 8f rank 2): the hyperopt-loop analogue ---------------------------------
 def test_model_selection_on_device_matches_oracle(engines):
     n, t, h = 600, 400, 28
