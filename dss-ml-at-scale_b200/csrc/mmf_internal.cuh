@@ -31,15 +31,18 @@ struct DesignView {
 // One series with gaps, handed to the thread-per-series solve kernel (256 B, indexed by row).
 // Missing grid positions come in two segments so that two producers (the two transform groups of the
 // tcgen05 kernel) can append without atomics: segment g holds nm[g] entries at miss_t[g*SOLVE_SEG ...].
-constexpr int SOLVE_SEG = 46;
+// Segments are a multiple of 4 entries and 8-B aligned: the solve kernel reads the positions four at a time.
+constexpr int SOLVE_SEG = 44;
 constexpr int SOLVE_MISS_CAP = 2 * SOLVE_SEG;
 struct SolveRec {
   float b[P];                              // moments A_fit^T (y - c) over the observed rows
   float c;                                 // centring constant
   uint16_t nm[2];                          // entries in each segment
-  uint16_t miss_t[SOLVE_MISS_CAP];         // grid positions of the missing fit rows
+  uint16_t miss_t[SOLVE_MISS_CAP];         // grid positions of the missing fit rows (byte offset 72)
+  uint16_t pad_[4];
 };
 static_assert(sizeof(SolveRec) == 256, "SolveRec is one 256-B record");
+static_assert(SOLVE_SEG % 4 == 0 && offsetof(SolveRec, miss_t) % 8 == 0, "position groups are aligned 8-B words");
 constexpr int MMF_STATUS_DEFERRED = -2;    // internal: the row's SolveRec is queued for solve_rows_kernel
 
 constexpr int MAX_OUT = 8;               // replicas of the forecast table one launch can write (one per GPU)

@@ -18,13 +18,36 @@ constexpr int THREADS = 128;
 
 __device__ __forceinline__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }   // i >= j
 
+__device__ __forceinline__ void ldg256_nc(const float* p, float4& lo, float4& hi) {      // p: 32-B aligned
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+               : "l"(p));
+}
+
+// both 128-B lines of a record into L1: the record is read piecemeal (moments, then one gap position at a time),
+// and every new 32-B sector would otherwise be its own trip to DRAM in the middle of the dependent chain
+__device__ __forceinline__ void prefetch_rec(const SolveRec* r) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(r));
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(r) + 128));
+}
+
 __global__ void __launch_bounds__(THREADS, 2)
 solve_rows_kernel(const DesignView d, const FitArgs a) {
   asm volatile("griddepcontrol.wait;" ::: "memory");    // programmatic dependent launch: the producer kernels are done
   const uint32_t count = min(*a.rec_count, a.rec_cap);
-  for (uint32_t i = blockIdx.x * THREADS + threadIdx.x; i < count; i += gridDim.x * THREADS) {
-    const int64_t row = a.rec_rows[i];
+  const uint32_t stride = gridDim.x * THREADS;
+  bool vec_out = (a.ld_out % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15u) == 0);
+  for (int q = 0; q + 1 < a.n_out; ++q) vec_out = vec_out && ((reinterpret_cast<uintptr_t>(a.out_more[q]) & 15u) == 0);
+  uint32_t i = blockIdx.x * THREADS + threadIdx.x;
+  int64_t row_next = i < count ? a.rec_rows[i] : 0;
+  if (i < count) prefetch_rec(a.recs + row_next);
+  for (; i < count; i += stride) {
+    const int64_t row = row_next;
     const SolveRec& rec = a.recs[row];
+    if (i + stride < count) {                           // the next series' record arrives while this one is solved
+      row_next = a.rec_rows[i + stride];
+      prefetch_rec(a.recs + row_next);
+    }
     float b[P];
     {
       const float4* bp = reinterpret_cast<const float4*>(rec.b);
@@ -43,16 +66,44 @@ solve_rows_kernel(const DesignView d, const FitArgs a) {
     for (int e = 0; e < NPAIR; ++e) G[e] = 0.f;
 #pragma unroll
     for (int j = 0; j < P; ++j) G[tri(j, j)] = ((d.kept_mask >> j) & 1u) ? 1.f : 0.f;
+    // software-pipelined: gap positions arrive four at a time (one 8-B load, two groups ahead) and the design row
+    // of the next gap is in flight while the 136 FMAs of the current one issue -- the load -> address -> load ->
+    // FMA chain and the L1 data pipe (every lane gathers its own addresses) were this kernel's limits
+    // every lane gathers a different 64-B design row: two 256-bit loads (one 32-B sector each) instead of four LDG.128
+    auto design_row = [&](int t, float4& r0, float4& r1, float4& r2, float4& r3) {
+      const float* ap = d.apred + (size_t)t * P;
+      ldg256_nc(ap, r0, r1);
+      ldg256_nc(ap + 8, r2, r3);
+    };
+    // (one flat loop over both segments, to pay the warp's max-over-lanes trip count once, measured slower:
+    //  the segment-switch bookkeeping costs more issue slots than the shorter trip count saves)
 #pragma unroll 1
-    for (int m = 0; m < nm0 + nm1; ++m) {
-      const int t = rec.miss_t[m < nm0 ? m : SOLVE_SEG + (m - nm0)];
-      const float4* ap = reinterpret_cast<const float4*>(d.apred + (size_t)t * P);
-      const float4 a0 = __ldg(ap), a1 = __ldg(ap + 1), a2 = __ldg(ap + 2), a3 = __ldg(ap + 3);
-      const float av[P] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
+    for (int seg = 0; seg < 2; ++seg) {
+      const int cnt = seg ? nm1 : nm0;
+      if (cnt == 0) continue;
+      const unsigned long long* grp = reinterpret_cast<const unsigned long long*>(rec.miss_t + seg * SOLVE_SEG);
+      const int n_grp = (cnt + 3) >> 2;
+      unsigned long long cur = grp[0];
+      unsigned long long nxt = n_grp > 1 ? grp[1] : 0ull;
+      float4 n0, n1, n2, n3;
+      design_row((int)(cur & 0xffffull), n0, n1, n2, n3);
+#pragma unroll 1
+      for (int m = 0; m < cnt; ++m) {
+        const float4 a0 = n0, a1 = n1, a2 = n2, a3 = n3;
+        const int k1 = (m + 1) & 3;
+        if (k1 == 0) {
+          cur = nxt;
+          const int gi = ((m + 1) >> 2) + 1;
+          nxt = gi < n_grp ? grp[gi] : 0ull;
+        }
+        // past the end: row 0 is a harmless filler (loaded, never used)
+        design_row(m + 1 < cnt ? (int)((cur >> (16 * k1)) & 0xffffull) : 0, n0, n1, n2, n3);
+        const float av[P] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
 #pragma unroll
-      for (int r = 0; r < P; ++r)
+        for (int r = 0; r < P; ++r)
 #pragma unroll
-        for (int q = 0; q <= r; ++q) G[tri(r, q)] = fmaf(-av[r], av[q], G[tri(r, q)]);
+          for (int q = 0; q <= r; ++q) G[tri(r, q)] = fmaf(-av[r], av[q], G[tri(r, q)]);
+      }
     }
 
     // ---- in-order right-looking Cholesky with pivot dropping (dropped column: L_jj = 1, rest 0)
@@ -101,10 +152,9 @@ solve_rows_kernel(const DesignView d, const FitArgs a) {
       gp[2] = make_float4(b[8], b[9], b[10], b[11]);  gp[3] = make_float4(b[12], b[13], b[14], b[15]);
       a.out_c[row] = c;
     }
-    // ---- forecasts
+    // ---- forecasts (16-B stores when the table allows it: a thread owns a whole row of it)
     const int64_t off = row * a.ld_out;
-#pragma unroll 1
-    for (int k = 0; k < (a.skip_pred ? 0 : a.n_pred); ++k) {
+    auto predict = [&](int k) -> float {
       const float4* ap = reinterpret_cast<const float4*>(d.apred + (size_t)(a.pred_start + k) * P);
       const float4 a0 = __ldg(ap), a1 = __ldg(ap + 1), a2 = __ldg(ap + 2), a3 = __ldg(ap + 3);
       float s = c;
@@ -112,8 +162,17 @@ solve_rows_kernel(const DesignView d, const FitArgs a) {
       s = fmaf(a1.x, b[4], s);  s = fmaf(a1.y, b[5], s);  s = fmaf(a1.z, b[6], s);  s = fmaf(a1.w, b[7], s);
       s = fmaf(a2.x, b[8], s);  s = fmaf(a2.y, b[9], s);  s = fmaf(a2.z, b[10], s); s = fmaf(a2.w, b[11], s);
       s = fmaf(a3.x, b[12], s); s = fmaf(a3.y, b[13], s); s = fmaf(a3.z, b[14], s); s = fmaf(a3.w, b[15], s);
-      store_out1(a, off + k, s);
+      return s;
+    };
+    const int n_pred = a.skip_pred ? 0 : a.n_pred;
+    int k = 0;
+    if (vec_out) {
+#pragma unroll 1
+      for (; k + 4 <= n_pred; k += 4)
+        store_out4(a, off + k, make_float4(predict(k), predict(k + 1), predict(k + 2), predict(k + 3)));
     }
+#pragma unroll 1
+    for (; k < n_pred; ++k) store_out1(a, off + k, predict(k));
     if (a.out_beta != nullptr) {
 #pragma unroll 1
       for (int p = 0; p < P; ++p) {

@@ -108,9 +108,37 @@ def test_parity_masked_series(engines, kernel):
     assert (np.abs(pred - want).max(axis=1) <= tol).all()
     assert np.array_equal(status, wst)
     if kernel != "warp":
-        # rows whose first value is missing (or with > 46 gaps per transform group) take the general pass;
+        # rows whose first value is missing (or with > 44 gaps per transform group) take the general pass;
         # every other gappy row is solved from the record the tcgen05 kernel queued
         assert 0 < res["stats"].n_pending < 300
+
+
+def test_gap_counts_around_record_capacity(engines):
+    """The tcgen05 kernel notes gap positions per transform group (alternate 32-step chunks) in two 44-entry
+    segments that the solve kernel reads four at a time: every count 0..48 in one group (all tails of the 4-wide
+    groups, the capacity edge and the overflow to the general pass), both groups, must match the oracle."""
+    t, h = 1095, 28
+    y0, start = mmf.synth.daily_store_item_demand(1, t, seed=21)
+    rows = []
+    for parity in (0, 1):
+        slots = np.array([p for p in range(1, t) if (p // 32) % 2 == parity])
+        rng = np.random.default_rng(parity)
+        for k in range(0, 49):
+            r = y0[0].copy()
+            r[rng.choice(slots, size=k, replace=False)] = np.nan
+            rows.append(r)
+    both = y0[0].copy()                                              # 44 in each group: the largest record
+    for parity in (0, 1):
+        slots = np.array([p for p in range(1, t) if (p // 32) % 2 == parity])
+        both[np.random.default_rng(7 + parity).choice(slots, size=44, replace=False)] = np.nan
+    rows.append(both)
+    y = np.stack(rows).astype(np.float32)
+    want, wst = O.fit_forecast_packed(y, *_design(start, t, h))
+    for k in ("auto", "tc"):
+        pred, status, res = _run(engines[k], y, start, "D", h, "future", want_stats=True)
+        assert np.array_equal(status, wst), k
+        assert np.abs(pred - want).max() <= tolerance(y), k
+        assert res["stats"].n_pending == 2 * 4, k                    # counts 45..48 of either group overflow
 
 
 def _design(start, t, h):
