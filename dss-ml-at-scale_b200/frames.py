@@ -81,20 +81,34 @@ class Bucket:
     t_len: int
     key_frame: pd.DataFrame      # one row per series, key columns only
     y: np.ndarray                # [n, t_len] float32 view of a pitched (pinned) buffer, NaN = missing
+    rank: np.ndarray | None = None       # position of each series in the key order of ALL groups of the call
+    key_arrow: dict | None = None        # Arrow front end: {key: pyarrow array of this bucket's n key values}
 
 
-def pack_groups(pdf: pd.DataFrame, keys=DEFAULT_KEYS, date_col="Date", value_col="Demand", freq="W-MON",
-                pinned: bool | None = None) -> list:
-    """Long frame -> calendar buckets of packed series (02:422-423 for all groups at once).
-    ``pinned=None`` page-locks buckets of >= 1 MiB (worth the cudaHostAlloc), False never."""
-    keys = list(keys)
+def _combine_codes(codes, sizes):
+    """Per-column codes (each numbering its column's values in sort order) -> (group id per row, per-column code
+    of every group), groups numbered in lexicographic key order.  Re-factorised after every column, so the
+    combined code never exceeds rows x cardinality."""
+    gid = np.asarray(codes[0], dtype=np.int64)
+    per_key = None                                     # [n_groups_so_far, columns_so_far]
+    for j in range(len(codes)):
+        if j == 0:
+            comb = gid
+        else:
+            comb = gid * np.int64(sizes[j]) + np.asarray(codes[j], dtype=np.int64)
+        gid, uniq = pd.factorize(comb, sort=True)
+        uniq = np.asarray(uniq, dtype=np.int64)
+        if j == 0:
+            per_key = uniq[:, None]
+        else:
+            per_key = np.concatenate([per_key[uniq // np.int64(sizes[j])], (uniq % np.int64(sizes[j]))[:, None]], axis=1)
+    return gid.astype(np.int64, copy=False), per_key
+
+
+def _pack_from_codes(gid, n_groups, days, vals, freq, pinned):
+    """Shared tail of the pandas and the Arrow packer: rows (group id, day, value) -> calendar buckets.
+    Returns [(start_day, t_len, members, y)] with ``members`` = the group ids of the bucket in key order."""
     step = D.FREQ_DAYS[freq]
-    if len(pdf) == 0:
-        return []
-    days = D.as_days(pdf[date_col].to_numpy()).astype(np.int64)
-    gid, uniq = pd.MultiIndex.from_frame(pdf[keys]).factorize(sort=True)
-    n_groups = len(uniq)
-    vals = pdf[value_col].to_numpy(dtype=np.float32, na_value=np.nan)
     gmin = np.full(n_groups, np.iinfo(np.int64).max)
     gmax = np.full(n_groups, np.iinfo(np.int64).min)
     np.minimum.at(gmin, gid, days)
@@ -105,24 +119,135 @@ def pack_groups(pdf: pd.DataFrame, keys=DEFAULT_KEYS, date_col="Date", value_col
     off = days - gmin[gid]
     on_grid = off % step == 0                       # off-grid rows vanish under asfreq
     pos = off // step
-    key_frame = pd.DataFrame(list(uniq), columns=keys)
-    buckets = []
+    out = []
     bucket_id, bucket_keys = pd.MultiIndex.from_arrays([gmin, t_len]).factorize(sort=True)
+    single = len(bucket_keys) == 1
     for b, (start_day, tl) in enumerate(bucket_keys):
-        members = np.flatnonzero(bucket_id == b)
-        local = np.full(n_groups, -1, dtype=np.int64)
-        local[members] = np.arange(members.size)
+        members = np.arange(n_groups) if single else np.flatnonzero(bucket_id == b)
         pin = (members.size * int(tl) * 4 >= (1 << 20)) if pinned is None else pinned
         y = alloc_packed(members.size, int(tl), pinned=pin)
         y[...] = np.nan
-        sel = on_grid & (local[gid] >= 0)
-        y[local[gid[sel]], pos[sel]] = vals[sel]
-        buckets.append(Bucket(np.datetime64(int(start_day), "D"), int(tl),
-                              key_frame.iloc[members].reset_index(drop=True), y))
+        if single:
+            y[gid[on_grid], pos[on_grid]] = vals[on_grid]
+        else:
+            local = np.full(n_groups, -1, dtype=np.int64)
+            local[members] = np.arange(members.size)
+            sel = on_grid & (local[gid] >= 0)
+            y[local[gid[sel]], pos[sel]] = vals[sel]
+        out.append((int(start_day), int(tl), members, y))
+    return out
+
+
+def pack_groups(pdf: pd.DataFrame, keys=DEFAULT_KEYS, date_col="Date", value_col="Demand", freq="W-MON",
+                pinned: bool | None = None) -> list:
+    """Long frame -> calendar buckets of packed series (02:422-423 for all groups at once).
+    ``pinned=None`` page-locks buckets of >= 1 MiB (worth the cudaHostAlloc), False never."""
+    keys = list(keys)
+    if len(pdf) == 0:
+        return []
+    days = D.as_days(pdf[date_col].to_numpy()).astype(np.int64)
+    codes, uniques = [], []
+    for k in keys:                                    # one hash pass per key column, never a tuple per row
+        c, u = pd.factorize(pdf[k], sort=True, use_na_sentinel=False)
+        codes.append(c)
+        uniques.append(u)
+    gid, per_key = _combine_codes(codes, [len(u) for u in uniques])
+    vals = pdf[value_col].to_numpy(dtype=np.float32, na_value=np.nan)
+    buckets = []
+    for start_day, tl, members, y in _pack_from_codes(gid, per_key.shape[0], days, vals, freq, pinned):
+        key_frame = pd.DataFrame({k: pd.Series(uniques[j].take(per_key[members, j]), dtype=pdf[k].dtype)
+                                  for j, k in enumerate(keys)})
+        buckets.append(Bucket(np.datetime64(start_day, "D"), tl, key_frame, y, rank=members))
+    return buckets
+
+
+def pack_table_host(table, keys=DEFAULT_KEYS, date_col="Date", value_col="Demand", freq="W-MON",
+                    pinned: bool | None = None) -> list:
+    """Arrow ``Table`` -> the same buckets as ``pack_groups`` without a pandas frame of the rows: key columns
+    are dictionary-encoded by Arrow, dates and values are read as NumPy views of the column buffers."""
+    import pyarrow as pa
+    import pyarrow.compute as pc
+
+    keys = list(keys)
+    if table.num_rows == 0:
+        return []
+    codes, uniques = [], []
+    for k in keys:
+        col = table.column(k)
+        col = col.combine_chunks() if isinstance(col, pa.ChunkedArray) else col
+        if not pa.types.is_dictionary(col.type):
+            col = pc.dictionary_encode(col, null_encoding="encode")
+        dic = col.dictionary
+        order = pc.sort_indices(dic).to_numpy()                      # dictionary is in first-seen order: rank it
+        rank = np.empty(len(dic), dtype=np.int64)
+        rank[order] = np.arange(len(dic))
+        idx = col.indices.to_numpy(zero_copy_only=False)
+        codes.append(rank[idx.astype(np.int64, copy=False)])
+        uniques.append(dic.take(pa.array(order)))
+    gid, per_key = _combine_codes(codes, [len(u) for u in uniques])
+    dcol = table.column(date_col).combine_chunks()
+    if not pa.types.is_date32(dcol.type):
+        dcol = pc.cast(dcol, pa.date32())
+    days = dcol.cast(pa.int32()).to_numpy(zero_copy_only=False).astype(np.int64)
+    vcol = pc.cast(table.column(value_col).combine_chunks(), pa.float32())
+    vals = vcol.fill_null(float("nan")).to_numpy(zero_copy_only=False) if vcol.null_count else vcol.to_numpy(zero_copy_only=False)
+    buckets = []
+    for start_day, tl, members, y in _pack_from_codes(gid, per_key.shape[0], days, vals, freq, pinned):
+        key_arrow = {k: uniques[j].take(pa.array(per_key[members, j])) for j, k in enumerate(keys)}
+        key_frame = pa.table(key_arrow).to_pandas()
+        buckets.append(Bucket(np.datetime64(start_day, "D"), tl, key_frame, y, rank=members, key_arrow=key_arrow))
     return buckets
 
 
 # ---- the drop-in UDF ---------------------------------------------------------------------------
+def _fit_buckets(buckets, eng, freq, horizon, mode, design, select, on_device):
+    """Run the engine over every bucket: yields (bucket, out_days, n_pred, y_host, pred_host)."""
+    for b in buckets:
+        out_days, pred_start, n_pred = eng.plan_calendar(b.start, b.t_len, freq, horizon, mode, design)
+        if select is not None:
+            if mode != "holdout":
+                raise ValueError("select= needs mode='holdout' (the held-out rows score the candidates)")
+            from .engine import device_packed
+            yd = b.y if on_device else device_packed(b.y)
+            pred = eng.fit_select_forecast(yd, horizon, tuple(select), pred_start, n_pred)["pred"].cpu().numpy()
+        else:
+            pred = eng.fit_forecast(b.y, pred_start, n_pred)
+            if on_device:
+                pred = pred.cpu().numpy()
+        y_host = b.y.cpu().numpy() if on_device else b.y
+        yield b, out_days, n_pred, y_host, pred
+
+
+def _global_order(buckets, keys, lengths):
+    """Row permutation that puts the concatenated per-bucket blocks into (key, date) order: a sort of one integer
+    per output row (the series' rank), never of the key strings."""
+    if all(b.rank is not None for b in buckets):
+        ranks = [np.asarray(b.rank, dtype=np.int64) for b in buckets]
+    else:                                               # e.g. device packer: rank the (few) key rows here
+        kf = pd.concat([b.key_frame for b in buckets], ignore_index=True)
+        order = kf.sort_values(list(keys), kind="stable").index.to_numpy()
+        r = np.empty(len(kf), dtype=np.int64)
+        r[order] = np.arange(len(kf))
+        cuts = np.cumsum([0] + [len(b.key_frame) for b in buckets])
+        ranks = [r[cuts[i]:cuts[i + 1]] for i in range(len(buckets))]
+    per_row = np.concatenate([np.repeat(rk, n) for rk, n in zip(ranks, lengths)])
+    return np.argsort(per_row, kind="stable")
+
+
+def _buckets_for(pdf, keys, date_col, value_col, freq, pack, eng):
+    import pyarrow as pa
+
+    if pack == "device":
+        from .packer import pack_table_device
+        return pack_table_device(pdf, keys, date_col, value_col, freq, engine=eng)
+    if pack != "host":
+        raise ValueError("pack must be 'host' or 'device'")
+    if isinstance(pdf, (pa.Table, pa.RecordBatch)):
+        return pack_table_host(pa.Table.from_batches([pdf]) if isinstance(pdf, pa.RecordBatch) else pdf,
+                               keys, date_col, value_col, freq)
+    return pack_groups(pdf, keys, date_col, value_col, freq)
+
+
 def forecast_groups(pdf, *, keys=DEFAULT_KEYS, date_col="Date", value_col="Demand",
                     freq="W-MON", horizon=FORECAST_HORIZON, mode="holdout", design="trend_season_exog",
                     engine: ForecastEngine | None = None, pack: str = "host", select=None) -> pd.DataFrame:
@@ -144,60 +269,66 @@ def forecast_groups(pdf, *, keys=DEFAULT_KEYS, date_col="Date", value_col="Deman
     eng = engine or default_engine()
     keys = list(keys)
     fitted_col = value_col + "_Fitted"
-    parts = []
-    if pack == "device":
-        from .packer import pack_table_device
-        buckets = pack_table_device(pdf, keys, date_col, value_col, freq, engine=eng)
-    elif pack == "host":
-        buckets = pack_groups(pdf, keys, date_col, value_col, freq)
-    else:
-        raise ValueError("pack must be 'host' or 'device'")
-    for b in buckets:
-        out_days, pred_start, n_pred = eng.plan_calendar(b.start, b.t_len, freq, horizon, mode, design)
-        if select is not None:
-            if mode != "holdout":
-                raise ValueError("select= needs mode='holdout' (the held-out rows score the candidates)")
-            from .engine import device_packed
-            yd = b.y if pack == "device" else device_packed(b.y)
-            pred = eng.fit_select_forecast(yd, horizon, tuple(select), pred_start, n_pred)["pred"]
-            pred = pred.cpu().numpy()
-            if pack == "device":
-                b.y = b.y.cpu().numpy()
-        else:
-            pred = eng.fit_forecast(b.y, pred_start, n_pred)
-            if pack == "device":
-                pred = pred.cpu().numpy()
-                b.y = b.y.cpu().numpy()
-        n = b.y.shape[0]
-        frame = {k: np.repeat(b.key_frame[k].to_numpy(), n_pred) for k in keys}
+    buckets = _buckets_for(pdf, keys, date_col, value_col, freq, pack, eng)
+    parts, lengths = [], []
+    for b, out_days, n_pred, y_host, pred in _fit_buckets(buckets, eng, freq, horizon, mode, design, select, pack == "device"):
+        n = y_host.shape[0]
+        row_of = np.repeat(np.arange(n), n_pred)
+        # key columns keep the dtype they came in with (no per-row string inference on N x T values)
+        frame = {k: pd.Series(b.key_frame[k].array.take(row_of), dtype=b.key_frame[k].dtype, copy=False) for k in keys}
         frame[date_col] = np.tile(out_days.astype("datetime64[ns]"), n)
         if mode == "holdout":
-            frame[value_col] = np.ascontiguousarray(b.y).reshape(-1)
+            frame[value_col] = np.ascontiguousarray(y_host).reshape(-1)
         else:
             frame[value_col] = np.full(n * n_pred, np.nan, dtype=np.float32)
         frame[fitted_col] = pred.reshape(-1)
         parts.append(pd.DataFrame(frame))
+        lengths.append(n_pred)
     if not parts:
         return pd.DataFrame({**{k: pd.Series(dtype=object) for k in keys},
                              date_col: pd.Series(dtype="datetime64[ns]"),
                              value_col: pd.Series(dtype=np.float32), fitted_col: pd.Series(dtype=np.float32)})
-    out = parts[0] if len(parts) == 1 else pd.concat(parts, ignore_index=True)
-    if len(parts) > 1:
-        out = out.sort_values(keys + [date_col], kind="stable", ignore_index=True)
-    return out
+    if len(parts) == 1:
+        return parts[0]
+    out = pd.concat(parts, ignore_index=True)
+    return out.take(_global_order(buckets, keys, lengths)).reset_index(drop=True)
 
 
-def forecast_table(table, **kw):
-    """Arrow ``Table``/``RecordBatch`` in -> Arrow ``Table`` with ``tuning_schema`` out
-    (the ``mapInArrow`` flavour of the boundary)."""
+def forecast_table(table, *, keys=DEFAULT_KEYS, date_col="Date", value_col="Demand",
+                   freq="W-MON", horizon=FORECAST_HORIZON, mode="holdout", design="trend_season_exog",
+                   engine: ForecastEngine | None = None, pack: str = "host", select=None):
+    """Arrow ``Table``/``RecordBatch`` in -> Arrow ``Table`` with ``tuning_schema`` out (the ``mapInArrow``
+    flavour of the boundary).  No pandas frame of the rows on either side: keys are dictionary-encoded on the way
+    in and expanded from a dictionary on the way out, dates and values are NumPy views of Arrow buffers."""
     import pyarrow as pa
 
     if isinstance(table, pa.RecordBatch):
         table = pa.Table.from_batches([table])
-    keys = kw.get("keys", DEFAULT_KEYS)
-    date_col, value_col = kw.get("date_col", "Date"), kw.get("value_col", "Demand")
-    out = forecast_groups(table if kw.get("pack") == "device" else table.to_pandas(), **kw)
-    return pa.Table.from_pandas(out, schema=tuning_schema(keys, date_col, value_col), preserve_index=False)
+    eng = engine or default_engine()
+    keys = list(keys)
+    schema = tuning_schema(keys, date_col, value_col)
+    buckets = _buckets_for(table, keys, date_col, value_col, freq, pack, eng)
+    parts, lengths = [], []
+    for b, out_days, n_pred, y_host, pred in _fit_buckets(buckets, eng, freq, horizon, mode, design, select, pack == "device"):
+        n = y_host.shape[0]
+        row_of = pa.array(np.repeat(np.arange(n, dtype=np.int32), n_pred))
+        cols = []
+        for k in keys:
+            kv = b.key_arrow[k] if b.key_arrow is not None else pa.array(b.key_frame[k].astype(str).to_numpy(dtype=object))
+            cols.append(pa.DictionaryArray.from_arrays(row_of, kv.cast(pa.string())).cast(pa.string()))
+        day32 = out_days.astype("datetime64[D]").astype(np.int32)
+        cols.append(pa.array(np.tile(day32, n)).cast(pa.date32()))
+        demand = (np.ascontiguousarray(y_host).reshape(-1) if mode == "holdout"
+                  else np.full(n * n_pred, np.nan, dtype=np.float32))
+        cols.append(pa.array(demand, from_pandas=True))               # NaN -> null, like the pandas route
+        cols.append(pa.array(np.ascontiguousarray(pred).reshape(-1), from_pandas=True))
+        parts.append(pa.Table.from_arrays(cols, schema=schema))
+        lengths.append(n_pred)
+    if not parts:
+        return schema.empty_table()
+    if len(parts) == 1:
+        return parts[0]
+    return pa.concat_tables(parts).combine_chunks().take(pa.array(_global_order(buckets, keys, lengths)))
 
 
 def forecast_arrow_batches(batches, **kw):

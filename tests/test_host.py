@@ -47,6 +47,80 @@ def test_pack_groups_daily_and_empty():
     assert b.t_len == 40 and np.array_equal(b.y[0], np.arange(40, dtype=np.float32))
 
 
+class _OracleEngine:
+    """Stands in for ForecastEngine where there is no GPU (test infrastructure only): same plan/fit interface."""
+
+    def plan_calendar(self, start, t_len, freq="D", horizon=28, mode="future", design="trend_season_exog"):
+        if mode == "holdout":
+            self.t_fit, n_rows, ps, npred = t_len - horizon, t_len, 0, t_len
+        else:
+            self.t_fit, n_rows, ps, npred = t_len, t_len + horizon, t_len, horizon
+        days = mmf.design.calendar_grid(start, n_rows, freq)
+        self.X = mmf.design.design_matrix(days, self.t_fit, design)
+        return days[ps:ps + npred], ps, npred
+
+    def fit_forecast(self, y, pred_start, n_pred, out=None):
+        from oracle import mmf_oracle as O
+        return O.fit_forecast_packed(np.asarray(y), self.X, self.t_fit, pred_start, n_pred)[0].astype(np.float32)
+
+
+def test_arrow_packer_equals_pandas_packer():
+    import pyarrow as pa
+    df = _frame()
+    df = df[~((df["SKU"] == "S1") & (df["Date"] == dt.date(2021, 1, 18)))].sample(frac=1.0, random_state=3)
+    host = mmf.pack_groups(df, freq="W-MON", pinned=False)
+    t = pa.Table.from_pandas(df, preserve_index=False)
+    for table in (t, t.set_column(1, "SKU", pa.array(df["SKU"]).dictionary_encode()),
+                  pa.Table.from_batches(t.to_batches(max_chunksize=7))):                 # chunked columns
+        got = mmf.frames.pack_table_host(table, freq="W-MON", pinned=False)
+        assert len(got) == len(host) == 2
+        for a, b in zip(got, host):
+            assert (a.start, a.t_len) == (b.start, b.t_len)
+            assert a.key_frame.to_numpy().tolist() == b.key_frame.to_numpy().tolist()
+            assert np.array_equal(a.y, b.y, equal_nan=True) and np.array_equal(a.rank, b.rank)
+
+
+def test_group_codes_many_key_columns_in_key_order():
+    rng = np.random.default_rng(0)
+    df = pd.DataFrame({"a": rng.integers(0, 4, 500), "b": rng.choice(list("xyz"), 500), "c": rng.integers(0, 3, 500),
+                       "Date": dt.date(2021, 1, 4), "Demand": 1.0}).drop_duplicates(["a", "b", "c"])
+    (b,) = mmf.pack_groups(df, keys=("a", "b", "c"), freq="W-MON", pinned=False)
+    want = df[["a", "b", "c"]].sort_values(["a", "b", "c"]).to_numpy().tolist()
+    assert b.key_frame.to_numpy().tolist() == want and b.key_frame["a"].dtype == df["a"].dtype
+
+
+def test_forecast_groups_and_table_buckets_in_key_order():
+    """Groups on different calendars (two buckets) come back interleaved in key order, dates ascending -- from the
+    pandas route and the Arrow route alike; the Arrow route returns tuning_schema with NaN as null."""
+    import pyarrow as pa
+    rows = []
+    for k, (start, n) in enumerate(((dt.date(2021, 1, 4), 30), (dt.date(2021, 2, 1), 26), (dt.date(2021, 1, 4), 30),
+                                    (dt.date(2021, 2, 1), 26))):
+        for i in range(n):
+            rows.append(("P%d" % (k % 2), "S%d" % k, start + dt.timedelta(weeks=i), float(50 * k + 3 * i + (i % 5))))
+    df = pd.DataFrame(rows, columns=["Product", "SKU", "Date", "Demand"])
+    df = df[~((df["SKU"] == "S2") & (df["Date"] == dt.date(2021, 3, 1)))].sample(frac=1.0, random_state=2)
+    kw = dict(horizon=4, mode="holdout", design="exog_only", engine=_OracleEngine())
+    out = mmf.forecast_groups(df, **kw)
+    assert list(out.columns) == ["Product", "SKU", "Date", "Demand", "Demand_Fitted"]
+    assert out["SKU"].tolist() == ["S0"] * 30 + ["S2"] * 30 + ["S1"] * 26 + ["S3"] * 26          # (Product, SKU) order
+    for _, g in out.groupby("SKU"):
+        assert g["Date"].is_monotonic_increasing
+    assert np.isnan(out[(out["SKU"] == "S2")]["Demand"].to_numpy()).sum() == 1
+    one = mmf.forecast_groups(df[df["SKU"] == "S3"], **kw)                               # a group alone == inside a batch
+    assert np.array_equal(one["Demand_Fitted"].to_numpy(), out[out["SKU"] == "S3"]["Demand_Fitted"].to_numpy())
+    tab = mmf.forecast_table(pa.Table.from_pandas(df, preserve_index=False), **kw)
+    assert tab.schema.equals(mmf.tuning_schema()) and tab.num_rows == len(out)
+    assert tab.column("SKU").to_pylist() == out["SKU"].tolist()
+    assert tab.column("Date").to_pylist() == [d.date() for d in out["Date"]]
+    assert tab.column("Demand").null_count == 1
+    assert np.array_equal(tab.column("Demand_Fitted").to_numpy(), out["Demand_Fitted"].to_numpy())
+    fut = mmf.forecast_table(pa.Table.from_pandas(df, preserve_index=False), horizon=4, mode="future",
+                             design="exog_only", engine=_OracleEngine())
+    assert fut.num_rows == 4 * 4 and fut.column("Demand").null_count == 16
+    assert mmf.forecast_table(pa.Table.from_pandas(df.iloc[:0], preserve_index=False), **kw).num_rows == 0
+
+
 def test_add_exo_variables_mirror(reference_fixtures):
     days = reference_fixtures["exo_weekly_days"].astype("datetime64[D]")
     pdf = pd.DataFrame({"Date": [dt.date.fromisoformat(str(d)) for d in days], "Product": "P", "SKU": "S",
