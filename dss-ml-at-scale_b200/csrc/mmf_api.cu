@@ -116,6 +116,8 @@ struct mmf_ctx {
   size_t c_cap_bytes = 0;
   int32_t* d_status_scratch = nullptr;
   size_t status_scratch_cap = 0;
+  void* d_pack_scratch = nullptr;      // sort / scan work space of the packer (grown on demand, kept)
+  size_t pack_scratch_cap = 0;
   Plan plan;
   Staging st[NBUF];
 };
@@ -333,6 +335,7 @@ int mmf_destroy(mmf_ctx* ctx) {
   cudaFree(ctx->d_gamma);
   cudaFree(ctx->d_c);
   cudaFree(ctx->d_status_scratch);
+  cudaFree(ctx->d_pack_scratch);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
   if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
@@ -707,7 +710,10 @@ int mmf_pack_group_codes(mmf_ctx* ctx, const uint64_t* hash, int64_t n, int32_t*
   PACK_PROLOGUE();
   if (!n_groups) return fail(MMF_E_INVALID, "n_groups is NULL");
   if (n > 0x7fffffff) return fail(MMF_E_UNSUPPORTED, "more than 2^31-1 rows in one pack call");
-  CU_TRY(pack_group_codes(hash, n, gid, first_row, n_groups, ctx->sm_count, ctx->stream));
+  size_t need = 0;
+  CU_TRY(pack_group_codes_scratch_bytes(n, &need));
+  if (int rc = grow(&ctx->d_pack_scratch, &ctx->pack_scratch_cap, need)) return rc;
+  CU_TRY(pack_group_codes(hash, n, gid, first_row, n_groups, ctx->d_pack_scratch, ctx->sm_count, ctx->stream));
   return MMF_OK;
 }
 

@@ -118,8 +118,9 @@ cudaError_t pack_verify_utf8(const int32_t* offsets, const uint8_t* data, int64_
                              const int32_t* first_row, uint64_t* mismatches, int sm, cudaStream_t s);
 cudaError_t pack_verify_i32(const int32_t* v, int64_t n, const int32_t* gid, const int32_t* first_row,
                             uint64_t* mismatches, int sm, cudaStream_t s);
+cudaError_t pack_group_codes_scratch_bytes(int64_t n, size_t* bytes);
 cudaError_t pack_group_codes(const uint64_t* h, int64_t n, int32_t* gid, int32_t* first_row, int32_t* n_groups_host,
-                             int sm, cudaStream_t s);
+                             void* scratch, int sm, cudaStream_t s);
 cudaError_t pack_minmax(const int32_t* gid, const int32_t* day, int64_t n, int32_t n_groups, int32_t* gmin,
                         int32_t* gmax, int sm, cudaStream_t s);
 cudaError_t pack_scatter(const int32_t* gid, const int32_t* day, const float* val, int64_t n,

@@ -162,40 +162,69 @@ cudaError_t pack_verify_i32(const int32_t* v, int64_t n, const int32_t* gid, con
   return cudaGetLastError();
 }
 
+// Scratch layout of pack_group_codes (the caller owns the buffer: no cudaMalloc / cudaFree on the packing path).
+namespace {
+struct CodesScratch {
+  size_t h_sorted, rows, rows_sorted, head, scan, tmp, tmp_bytes, total;
+};
+inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+cudaError_t codes_scratch_layout(int64_t n, CodesScratch* L) {
+  size_t tmp_sort = 0, tmp_scan = 0;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, (const uint64_t*)nullptr, (uint64_t*)nullptr,
+                                                  (const int32_t*)nullptr, (int32_t*)nullptr, (int)n, 0, 64);
+  if (e != cudaSuccess) return e;
+  e = cub::DeviceScan::InclusiveSum(nullptr, tmp_scan, (const int32_t*)nullptr, (int32_t*)nullptr, (int)n);
+  if (e != cudaSuccess) return e;
+  size_t off = 0;
+  L->h_sorted = off;    off += align256((size_t)n * sizeof(uint64_t));
+  L->rows = off;        off += align256((size_t)n * sizeof(int32_t));
+  L->rows_sorted = off; off += align256((size_t)n * sizeof(int32_t));
+  L->head = off;        off += align256((size_t)n * sizeof(int32_t));
+  L->scan = off;        off += align256((size_t)n * sizeof(int32_t));
+  L->tmp = off;
+  L->tmp_bytes = std::max(tmp_sort, tmp_scan);
+  L->total = off + align256(L->tmp_bytes);
+  return cudaSuccess;
+}
+}  // namespace
+
+cudaError_t pack_group_codes_scratch_bytes(int64_t n, size_t* bytes) {
+  CodesScratch L{};
+  *bytes = 0;
+  if (n <= 0) return cudaSuccess;
+  cudaError_t e = codes_scratch_layout(n, &L);
+  *bytes = L.total;
+  return e;
+}
+
 // hash[n] -> gid[n] (dense codes in hash order), first_row[>= n_groups], *n_groups.  Synchronises once (to read G).
+// `scratch` holds pack_group_codes_scratch_bytes(n) bytes of device memory.
 cudaError_t pack_group_codes(const uint64_t* h, int64_t n, int32_t* gid, int32_t* first_row, int32_t* n_groups_host,
-                             int sm, cudaStream_t s) {
+                             void* scratch, int sm, cudaStream_t s) {
   *n_groups_host = 0;
   if (n <= 0) return cudaSuccess;
-  uint64_t* h_sorted = nullptr;
-  int32_t *rows = nullptr, *rows_sorted = nullptr, *head = nullptr, *scan = nullptr;
-  void* tmp = nullptr;
-  size_t tmp_sort = 0, tmp_scan = 0;
-  cudaError_t e;
-  auto cleanup = [&]() {
-    cudaFree(h_sorted); cudaFree(rows); cudaFree(rows_sorted); cudaFree(head); cudaFree(scan); cudaFree(tmp);
-  };
-#define PK_TRY(x) do { e = (x); if (e != cudaSuccess) { cleanup(); return e; } } while (0)
-  PK_TRY(cudaMalloc(&h_sorted, n * sizeof(uint64_t)));
-  PK_TRY(cudaMalloc(&rows, n * sizeof(int32_t)));
-  PK_TRY(cudaMalloc(&rows_sorted, n * sizeof(int32_t)));
-  PK_TRY(cudaMalloc(&head, n * sizeof(int32_t)));
-  PK_TRY(cudaMalloc(&scan, n * sizeof(int32_t)));
-  PK_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, h, h_sorted, rows, rows_sorted, (int)n, 0, 64, s));
-  PK_TRY(cub::DeviceScan::InclusiveSum(nullptr, tmp_scan, head, scan, (int)n, s));
-  PK_TRY(cudaMalloc(&tmp, std::max(tmp_sort, tmp_scan)));
+  CodesScratch L{};
+  cudaError_t e = codes_scratch_layout(n, &L);
+  if (e != cudaSuccess) return e;
+  char* base = static_cast<char*>(scratch);
+  uint64_t* h_sorted = reinterpret_cast<uint64_t*>(base + L.h_sorted);
+  int32_t* rows = reinterpret_cast<int32_t*>(base + L.rows);
+  int32_t* rows_sorted = reinterpret_cast<int32_t*>(base + L.rows_sorted);
+  int32_t* head = reinterpret_cast<int32_t*>(base + L.head);
+  int32_t* scan = reinterpret_cast<int32_t*>(base + L.scan);
+  void* tmp = base + L.tmp;
+#define PK_TRY(x) do { e = (x); if (e != cudaSuccess) return e; } while (0)
   iota_kernel<<<grid_for(n, sm), TPB, 0, s>>>(rows, n);
-  size_t t1 = tmp_sort;
+  size_t t1 = L.tmp_bytes;
   PK_TRY(cub::DeviceRadixSort::SortPairs(tmp, t1, h, h_sorted, rows, rows_sorted, (int)n, 0, 64, s));
   heads_kernel<<<grid_for(n, sm), TPB, 0, s>>>(h_sorted, n, head);
-  size_t t2 = tmp_scan;
+  size_t t2 = L.tmp_bytes;
   PK_TRY(cub::DeviceScan::InclusiveSum(tmp, t2, head, scan, (int)n, s));
   codes_kernel<<<grid_for(n, sm), TPB, 0, s>>>(scan, head, rows_sorted, n, gid, first_row);
   PK_TRY(cudaGetLastError());
   PK_TRY(cudaMemcpyAsync(n_groups_host, scan + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   PK_TRY(cudaStreamSynchronize(s));
 #undef PK_TRY
-  cleanup();
   return cudaSuccess;
 }
 

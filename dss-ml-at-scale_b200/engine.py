@@ -12,6 +12,7 @@ plumbing here (device memory / streams); all arithmetic is in ``libmmf.so``.
 from __future__ import annotations
 
 import ctypes as C
+import threading
 import weakref
 from dataclasses import dataclass
 
@@ -45,18 +46,63 @@ def _describe(x, name: str):
     return a.ctypes.data, a.shape[0], a.shape[1], a.strides[0] // a.itemsize
 
 
+class _PinnedPool:
+    """Page-locked blocks are expensive on both ends (cudaHostAlloc ~ 0.5 ms/MB, cudaFreeHost more): blocks a
+    NumPy view no longer references go back to a small free list (capped) instead of to the driver, so a worker
+    that packs one batch after another pins its staging memory once."""
+    MAX_BYTES = 4 << 30
+    MAX_BLOCKS = 8
+
+    def __init__(self):
+        self.free = []                       # [(size, address)]
+        self.lock = threading.Lock()
+
+    def take(self, lib, nbytes):
+        gran = max(4096, 1 << max(0, nbytes.bit_length() - 4))          # <= 6 % over-allocation
+        size = -(-nbytes // gran) * gran
+        with self.lock:
+            fits = [blk for blk in self.free if size <= blk[0] <= size + size // 4]
+            if fits:
+                blk = min(fits)
+                self.free.remove(blk)
+                return blk[1], blk[0]
+        p = C.c_void_p()
+        N.check(lib.mmf_alloc_pinned(size, C.byref(p)))
+        return p.value, size
+
+    def give(self, lib, addr, size):
+        with self.lock:
+            if len(self.free) < self.MAX_BLOCKS and sum(b[0] for b in self.free) + size <= self.MAX_BYTES:
+                self.free.append((size, addr))
+                return
+        lib.mmf_free_pinned(addr)
+
+    def clear(self, lib):
+        with self.lock:
+            blocks, self.free = self.free, []
+        for _, addr in blocks:
+            lib.mmf_free_pinned(addr)
+
+
+_pinned_pool = _PinnedPool()
+
+
 def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
     """NumPy array over page-locked host memory (``mmf_alloc_pinned``): the Arrow/NumPy ->
-    device hop becomes one ``cudaMemcpyAsync`` per chunk."""
+    device hop becomes one ``cudaMemcpyAsync`` per chunk.  Blocks are recycled through a small pool."""
     lib = N.load()
     dtype = np.dtype(dtype)
-    nbytes = int(np.prod(shape)) * dtype.itemsize
-    p = C.c_void_p()
-    N.check(lib.mmf_alloc_pinned(max(nbytes, 1), C.byref(p)))
-    buf = (C.c_byte * max(nbytes, 1)).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-    weakref.finalize(buf, lib.mmf_free_pinned, p.value)
+    count = int(np.prod(shape))
+    addr, size = _pinned_pool.take(lib, max(count * dtype.itemsize, 1))
+    buf = (C.c_byte * size).from_address(addr)
+    arr = np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+    weakref.finalize(buf, _pinned_pool.give, lib, addr, size)
     return arr
+
+
+def release_pinned_pool() -> None:
+    """Hand the recycled page-locked blocks back to the driver."""
+    _pinned_pool.clear(N.load())
 
 
 def device_packed(y, device="cuda"):

@@ -74,6 +74,66 @@ def split_train_score_data(data, forecast_horizon: int = FORECAST_HORIZON):
 
 
 # ---- packing ---------------------------------------------------------------------------------
+import os as _os
+
+PARALLEL_MIN_ROWS = int(_os.environ.get("MMF_PARALLEL_MIN_ROWS", 8_000_000))   # below: Arrow string kernels stay on the calling thread
+
+
+def _n_threads() -> int:
+    import os
+
+    return max(1, min(16, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
+
+
+def _parallel(fn, items):
+    """Arrow compute kernels release the GIL: string hashing / expansion of a big column runs on a few threads."""
+    if len(items) <= 1 or _n_threads() == 1:
+        return [fn(it) for it in items]
+    from concurrent.futures import ThreadPoolExecutor
+
+    with ThreadPoolExecutor(_n_threads()) as ex:
+        return list(ex.map(fn, items))
+
+
+def _slices(n, k):
+    cuts = np.linspace(0, n, k + 1).astype(np.int64)
+    return [(int(cuts[i]), int(cuts[i + 1])) for i in range(k) if cuts[i + 1] > cuts[i]]
+
+
+def _dictionary_encode(col):
+    """Arrow column (Array or ChunkedArray) -> one DictionaryArray (nulls encoded as a value); big columns are
+    hashed piecewise on several threads and the dictionaries unified."""
+    import pyarrow as pa
+    import pyarrow.compute as pc
+
+    n = len(col)
+    chunks = col.chunks if isinstance(col, pa.ChunkedArray) else [col]
+    if chunks and pa.types.is_dictionary(chunks[0].type):
+        return col.unify_dictionaries().combine_chunks() if isinstance(col, pa.ChunkedArray) else col
+    if n >= PARALLEL_MIN_ROWS and _n_threads() > 1:
+        if len(chunks) < 2:
+            arr = chunks[0]
+            chunks = [arr.slice(a, b - a) for a, b in _slices(n, _n_threads())]
+        parts = _parallel(lambda c: pc.dictionary_encode(c, null_encoding="encode"), chunks)
+        return pa.chunked_array(parts).unify_dictionaries().combine_chunks()
+    arr = col.combine_chunks() if isinstance(col, pa.ChunkedArray) else col
+    return pc.dictionary_encode(arr, null_encoding="encode")
+
+
+def _expand_strings(values, row_of: np.ndarray):
+    """``values[row_of]`` as an Arrow string column, built from a dictionary (never one Python string per row)."""
+    import pyarrow as pa
+
+    values = values.cast(pa.string())
+
+    def piece(ab):
+        return pa.DictionaryArray.from_arrays(pa.array(row_of[ab[0]:ab[1]]), values).cast(pa.string())
+
+    if row_of.size >= PARALLEL_MIN_ROWS and _n_threads() > 1:
+        return pa.chunked_array(_parallel(piece, _slices(row_of.size, _n_threads())), type=pa.string())
+    return piece((0, row_of.size))
+
+
 @dataclass
 class Bucket:
     """Groups that share one calendar (same first date, same grid length)."""
@@ -87,15 +147,27 @@ class Bucket:
 
 def _combine_codes(codes, sizes):
     """Per-column codes (each numbering its column's values in sort order) -> (group id per row, per-column code
-    of every group), groups numbered in lexicographic key order.  Re-factorised after every column, so the
-    combined code never exceeds rows x cardinality."""
+    of every group), groups numbered in lexicographic key order.  One hash pass over a mixed-radix code when the
+    product of the cardinalities fits 62 bits, else re-factorised column by column."""
+    sizes = [max(int(z), 1) for z in sizes]
+    total = 1
+    for z in sizes:
+        total *= z
+    if total < (1 << 62):
+        comb = np.asarray(codes[0], dtype=np.int64)
+        for j in range(1, len(codes)):
+            comb = comb * np.int64(sizes[j]) + np.asarray(codes[j], dtype=np.int64)
+        gid, uniq = pd.factorize(comb, sort=True)
+        uniq = np.asarray(uniq, dtype=np.int64)
+        cols = []
+        for j in range(len(codes) - 1, -1, -1):
+            cols.append(uniq % np.int64(sizes[j]))
+            uniq = uniq // np.int64(sizes[j])
+        return gid.astype(np.int64, copy=False), np.stack(cols[::-1], axis=1)
     gid = np.asarray(codes[0], dtype=np.int64)
     per_key = None                                     # [n_groups_so_far, columns_so_far]
     for j in range(len(codes)):
-        if j == 0:
-            comb = gid
-        else:
-            comb = gid * np.int64(sizes[j]) + np.asarray(codes[j], dtype=np.int64)
+        comb = gid if j == 0 else gid * np.int64(sizes[j]) + np.asarray(codes[j], dtype=np.int64)
         gid, uniq = pd.factorize(comb, sort=True)
         uniq = np.asarray(uniq, dtype=np.int64)
         if j == 0:
@@ -109,16 +181,16 @@ def _pack_from_codes(gid, n_groups, days, vals, freq, pinned):
     """Shared tail of the pandas and the Arrow packer: rows (group id, day, value) -> calendar buckets.
     Returns [(start_day, t_len, members, y)] with ``members`` = the group ids of the bucket in key order."""
     step = D.FREQ_DAYS[freq]
-    gmin = np.full(n_groups, np.iinfo(np.int64).max)
-    gmax = np.full(n_groups, np.iinfo(np.int64).min)
-    np.minimum.at(gmin, gid, days)
-    np.maximum.at(gmax, gid, days)
+    span = pd.Series(days).groupby(gid, sort=True).agg(["min", "max"])       # gid is dense: row g = group g
+    gmin, gmax = span["min"].to_numpy(dtype=np.int64), span["max"].to_numpy(dtype=np.int64)
     if freq == "W-MON" and np.any((gmin + 3) % 7 != 0):
         raise ValueError("W-MON series must start on a Monday")
     t_len = (gmax - gmin) // step + 1
     off = days - gmin[gid]
-    on_grid = off % step == 0                       # off-grid rows vanish under asfreq
     pos = off // step
+    on_grid = None if step == 1 else (off % step == 0)                       # off-grid rows vanish under asfreq
+    if on_grid is not None and on_grid.all():
+        on_grid = None
     out = []
     bucket_id, bucket_keys = pd.MultiIndex.from_arrays([gmin, t_len]).factorize(sort=True)
     single = len(bucket_keys) == 1
@@ -127,13 +199,20 @@ def _pack_from_codes(gid, n_groups, days, vals, freq, pinned):
         pin = (members.size * int(tl) * 4 >= (1 << 20)) if pinned is None else pinned
         y = alloc_packed(members.size, int(tl), pinned=pin)
         y[...] = np.nan
+        ld = y.strides[0] // 4
+        flat = np.lib.stride_tricks.as_strided(y, shape=(members.size * ld,), strides=(4,))   # the pitched rows, 1-D
         if single:
-            y[gid[on_grid], pos[on_grid]] = vals[on_grid]
+            row, sel = gid, on_grid
         else:
             local = np.full(n_groups, -1, dtype=np.int64)
             local[members] = np.arange(members.size)
-            sel = on_grid & (local[gid] >= 0)
-            y[local[gid[sel]], pos[sel]] = vals[sel]
+            row = local[gid]
+            sel = (row >= 0) if on_grid is None else (on_grid & (row >= 0))
+        idx = row * ld + pos
+        if sel is None:
+            flat[idx] = vals
+        else:
+            flat[idx[sel]] = vals[sel]
         out.append((int(start_day), int(tl), members, y))
     return out
 
@@ -173,10 +252,7 @@ def pack_table_host(table, keys=DEFAULT_KEYS, date_col="Date", value_col="Demand
         return []
     codes, uniques = [], []
     for k in keys:
-        col = table.column(k)
-        col = col.combine_chunks() if isinstance(col, pa.ChunkedArray) else col
-        if not pa.types.is_dictionary(col.type):
-            col = pc.dictionary_encode(col, null_encoding="encode")
+        col = _dictionary_encode(table.column(k))
         dic = col.dictionary
         order = pc.sort_indices(dic).to_numpy()                      # dictionary is in first-seen order: rank it
         rank = np.empty(len(dic), dtype=np.int64)
@@ -311,11 +387,11 @@ def forecast_table(table, *, keys=DEFAULT_KEYS, date_col="Date", value_col="Dema
     parts, lengths = [], []
     for b, out_days, n_pred, y_host, pred in _fit_buckets(buckets, eng, freq, horizon, mode, design, select, pack == "device"):
         n = y_host.shape[0]
-        row_of = pa.array(np.repeat(np.arange(n, dtype=np.int32), n_pred))
+        row_of = np.repeat(np.arange(n, dtype=np.int32), n_pred)
         cols = []
         for k in keys:
             kv = b.key_arrow[k] if b.key_arrow is not None else pa.array(b.key_frame[k].astype(str).to_numpy(dtype=object))
-            cols.append(pa.DictionaryArray.from_arrays(row_of, kv.cast(pa.string())).cast(pa.string()))
+            cols.append(_expand_strings(kv, row_of))
         day32 = out_days.astype("datetime64[D]").astype(np.int32)
         cols.append(pa.array(np.tile(day32, n)).cast(pa.date32()))
         demand = (np.ascontiguousarray(y_host).reshape(-1) if mode == "holdout"
