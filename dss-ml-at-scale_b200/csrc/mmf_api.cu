@@ -204,8 +204,14 @@ int run_device(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, int32_t pr
   uint32_t* counters = ctx->d_pending + 2 * cs;
   ctx->counter_set ^= 1;
   if (may_mask) a.rec_count = counters + 1;
-  if (kernel == MMF_KERNEL_TC) a.zero_next = ctx->d_pending + 2 * (cs ^ 1);
-  else {
+  // Under stream capture the launches become a graph that is replayed with THIS counter set every time, so the
+  // set cannot rely on the previous call having zeroed it: the graph gets its own memset node.
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  CU_TRY(cudaStreamIsCapturing(s, &cap));
+  if (kernel == MMF_KERNEL_TC) {
+    a.zero_next = ctx->d_pending + 2 * (cs ^ 1);
+    if (cap != cudaStreamCaptureStatusNone) CU_TRY(cudaMemsetAsync(counters, 0, 2 * sizeof(uint32_t), s));
+  } else {
     CU_TRY(cudaMemsetAsync(ctx->d_pending, 0, 4 * sizeof(uint32_t), s));
   }
   if (kernel == MMF_KERNEL_TC) {

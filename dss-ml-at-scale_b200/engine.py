@@ -266,6 +266,27 @@ class ForecastEngine:
         return res
 
 
+    def capture(self, y, pred_start: int, n_pred: int, out=None, status=None):
+        """Record one device-resident ``fit_forecast`` call as a CUDA graph.  Small batches are launch-bound (three
+        kernel launches plus the Python/ctypes hop cost more than the kernels themselves): ``graph.replay()``
+        re-runs the whole fit on whatever ``y`` holds at that time and overwrites ``out`` / ``status``.
+        Returns ``(graph, out)``.  torch provides the graph object; every node in it is a libmmf kernel."""
+        import torch
+        if not (_is_torch(y) and y.is_cuda):
+            raise ValueError("capture() needs a CUDA tensor")
+        n = y.shape[0]
+        if out is None:
+            out = torch.empty((n, (n_pred + 3) & ~3), device=y.device, dtype=torch.float32)[:, :n_pred]
+        if status is None:
+            status = torch.empty(n, device=y.device, dtype=torch.int32)
+        self.fit_forecast(y, pred_start, n_pred, out=out, status=status)    # sizes the library's scratch outside capture
+        torch.cuda.synchronize(y.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.fit_forecast(y, pred_start, n_pred, out=out, status=status)
+        self.set_stream(torch.cuda.current_stream(y.device).cuda_stream)
+        return graph, out
+
     def fit_select_forecast(self, y, n_hold: int, candidates=(1, 3, 9, 13, 16), pred_start: int = 0,
                             n_pred: int | None = None):
         """Per-series model selection on the device (reference: the hyperopt loop + refit, 02:435-488).
