@@ -242,6 +242,7 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
     bool bad = collect && !finite(c);                   // cannot centre on a missing first value: general path
     if (bad) c = 0.f;
     int nm = 0;                                         // missing values this thread saw in the current tile
+    unsigned long long packq = 0ull;                    // the last (nm & 3) gap positions, newest in the top lanes
     int lt = 0;                                         // local tile counter (s_nm ring slot)
     while (tile < n_tiles) {
       mbar_wait(bar_full(stage), phase);
@@ -268,13 +269,16 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
             v[q].x = f0 ? v[q].x : c;  v[q].y = f1 ? v[q].y : c;      // contributes (c - c) = 0 to every moment
             v[q].z = f2 ? v[q].z : c;  v[q].w = f3 ? v[q].w : c;
           }
+          // positions are shifted into a 64-bit register and leave four at a time (one 8-B store, the unit the
+          // solve kernel reads): a 2-B store per gap made the record traffic the limiter of the gappy case
           uint16_t* __restrict__ mt = a.recs[(int64_t)tile * TILE_M + r].miss_t + grp * SOLVE_SEG;
           const int tbase = ch * KC;
           while (gaps) {
             const int pos = __ffs(gaps) - 1;
             gaps &= gaps - 1u;
-            if (nm < SOLVE_SEG) mt[nm] = static_cast<uint16_t>(tbase + pos);
+            packq = (packq >> 16) | (static_cast<unsigned long long>(tbase + pos) << 48);
             ++nm;
+            if ((nm & 3) == 0 && nm <= SOLVE_SEG) *reinterpret_cast<unsigned long long*>(mt + nm - 4) = packq;
           }
         }
       }
@@ -299,6 +303,10 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
       tmem_st_32x32b_x32(a_hi + 32, lo);
       const bool last_own = collect && ch + NGROUPS >= n_chunks;       // my last chunk of this tile
       if (last_own) {
+        if ((nm & 3) != 0 && nm < SOLVE_SEG) {          // flush the partial group (right-aligned: oldest first)
+          uint16_t* __restrict__ mt = a.recs[(int64_t)tile * TILE_M + r].miss_t + grp * SOLVE_SEG;
+          *reinterpret_cast<unsigned long long*>(mt + (nm & ~3)) = packq >> (16 * (4 - (nm & 3)));
+        }
         const int cnt = nm > 0x7ffe ? 0x7ffe : nm;
         s_nm[((lt & (NM_RING - 1)) * NGROUPS + grp) * TILE_M + r] = static_cast<uint16_t>(cnt | (bad ? 0x8000 : 0));
       }
