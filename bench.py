@@ -221,6 +221,8 @@ def run_ours(args):
         print(f"# note: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    all_cpus = os.sched_getaffinity(0)
+    numa_cpus = mmf.bind_to_gpu_numa(local)             # pinned staging buffers land on the GPU's NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n, t, h = args.series, args.t, args.horizon
@@ -411,10 +413,12 @@ def run_ours(args):
         e2e = {"value": world * ne * Ke / te, "unit": UNIT, "h2d_bytes_per_step": ne * t * 4,
                "d2h_bytes_per_step": ne * h * 4, "series_per_step_per_gpu": ne, "steps": Ke,
                "ms_per_step": 1e3 * te / Ke, "max_abs_diff_vs_device_path": chk,
-               "api": "mmf_fit_forecast_f32 with pinned host y/out (ForecastEngine.fit_forecast on NumPy arrays)"}
+               "api": "mmf_fit_forecast_f32 with pinned host y/out (ForecastEngine.fit_forecast on NumPy arrays)",
+               "cpu_affinity": (f"{len(numa_cpus)} cores local to the GPU (NVML)" if numa_cpus else "unchanged")}
         eng2.close()
 
     cpu = None
+    os.sched_setaffinity(0, all_cpus)                   # the CPU legs use every host core again
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_port_baseline(y[:100000].cpu().numpy(), start, t, h)
 
