@@ -180,11 +180,17 @@ class ForecastEngine:
                                           1 if has_constant else 0))
         self.t_fit = int(t_fit)
         self.n_rows = int(X.shape[0])
+        self._calendar_key = None
 
     def plan_calendar(self, start, t_len: int, freq: str = "D", horizon: int = 28, mode: str = "future",
                       design: str = "trend_season_exog"):
         """Build and plan the design for a bucket of series that start at ``start`` and have
-        ``t_len`` grid rows.  Returns ``(dates_of_prediction_rows, pred_start, n_pred)``."""
+        ``t_len`` grid rows.  Returns ``(dates_of_prediction_rows, pred_start, n_pred)``.
+        The calendar planned last is remembered: the literal drop-in (one group per call, every group on the same
+        calendar, 02:523-528) whitens and uploads its design once per worker, not once per group."""
+        key = (str(np.datetime64(start, "D")), int(t_len), freq, int(horizon), mode, design)
+        if getattr(self, "_calendar_key", None) == key:
+            return self._calendar_plan
         if mode == "holdout":                       # reference semantics, 02:372-380 + 484-488
             t_fit = t_len - horizon
             if t_fit < 1:
@@ -199,7 +205,9 @@ class ForecastEngine:
             raise ValueError(f"mode must be 'holdout' or 'future', got {mode!r}")
         X = D.design_matrix(days, t_fit, design)
         self.plan(X, t_fit, D.design_has_constant(design))
-        return days[pred_start:pred_start + n_pred], pred_start, n_pred
+        self._calendar_key = key
+        self._calendar_plan = (days[pred_start:pred_start + n_pred], pred_start, n_pred)
+        return self._calendar_plan
 
     def whitening(self):
         W = np.zeros((N.MMF_P, N.MMF_P), dtype=np.float64)

@@ -181,8 +181,16 @@ def _pack_from_codes(gid, n_groups, days, vals, freq, pinned):
     """Shared tail of the pandas and the Arrow packer: rows (group id, day, value) -> calendar buckets.
     Returns [(start_day, t_len, members, y)] with ``members`` = the group ids of the bucket in key order."""
     step = D.FREQ_DAYS[freq]
-    span = pd.Series(days).groupby(gid, sort=True).agg(["min", "max"])       # gid is dense: row g = group g
-    gmin, gmax = span["min"].to_numpy(dtype=np.int64), span["max"].to_numpy(dtype=np.int64)
+    if n_groups == 1:                                                        # the one-group-per-call drop-in
+        gmin, gmax = np.array([days.min()], dtype=np.int64), np.array([days.max()], dtype=np.int64)
+    elif days.size < 50_000:
+        gmin = np.full(n_groups, np.iinfo(np.int64).max)
+        gmax = np.full(n_groups, np.iinfo(np.int64).min)
+        np.minimum.at(gmin, gid, days)
+        np.maximum.at(gmax, gid, days)
+    else:
+        span = pd.Series(days).groupby(gid, sort=True).agg(["min", "max"])   # gid is dense: row g = group g
+        gmin, gmax = span["min"].to_numpy(dtype=np.int64), span["max"].to_numpy(dtype=np.int64)
     if freq == "W-MON" and np.any((gmin + 3) % 7 != 0):
         raise ValueError("W-MON series must start on a Monday")
     t_len = (gmax - gmin) // step + 1
@@ -192,7 +200,9 @@ def _pack_from_codes(gid, n_groups, days, vals, freq, pinned):
     if on_grid is not None and on_grid.all():
         on_grid = None
     out = []
-    bucket_id, bucket_keys = pd.MultiIndex.from_arrays([gmin, t_len]).factorize(sort=True)
+    # buckets in (first day, length) order: one sortable integer per group
+    uniq, bucket_id = np.unique(gmin * np.int64(1 << 32) + t_len, return_inverse=True)
+    bucket_keys = [(int(u >> 32), int(u & 0xFFFFFFFF)) for u in uniq.tolist()]
     single = len(bucket_keys) == 1
     for b, (start_day, tl) in enumerate(bucket_keys):
         members = np.arange(n_groups) if single else np.flatnonzero(bucket_id == b)

@@ -48,6 +48,15 @@ def main():
             ref = fitted
         res[name] = {"seconds": best, "rows_per_s": len(df) / best, "groups_per_s": G / best,
                      "max_abs_diff_vs_pandas_route": float(np.abs(fitted - ref).max())}
+    # the literal drop-in: one call per group, as applyInPandas(forecast_groups) makes them (02:523-528)
+    parts = [g for _, g in df[df["SKU"].isin(sku[:300])].groupby(["Product", "SKU"], sort=False)]
+    mmf.forecast_groups(parts[0], engine=eng)
+    t0 = time.perf_counter()
+    for g in parts:
+        mmf.forecast_groups(g, engine=eng)
+    dt = time.perf_counter() - t0
+    res["one_group_per_call"] = {"calls": len(parts), "seconds": dt, "groups_per_s": len(parts) / dt,
+                                 "ms_per_call": 1e3 * dt / len(parts)}
     print(json.dumps(res))
 
 
