@@ -222,6 +222,39 @@ def test_bridge_to_reference_model_family_statsmodels():
     assert np.abs(fc.to_numpy() - ours["Demand_Fitted"].to_numpy()[117:]).max() <= 1e-3 * float(one["Demand"].max())
 
 
+def test_reference_objective_optimum_is_the_oracle_fit():
+    """The reference maximises the Gaussian likelihood of SARIMAX(p,d,q)+exog with Nelder-Mead
+    (``model.fit(disp=False, method='nm')``, 02:441-450, 472-481).  At the (0,0,0) corner of its search space that
+    likelihood is  -n/2 log(2 pi s2) - |y - X b|^2 / (2 s2)  in (b, s2): two independent third-party solvers
+    (SciPy's Nelder-Mead on exactly that objective, started from the oracle's answer and from a perturbed point, and
+    scikit-learn's least squares) must agree with the oracle's exog_only fit -- the closed form is the optimum the
+    reference's optimiser is searching for."""
+    from scipy.optimize import minimize
+    from sklearn.linear_model import LinearRegression
+    df = mmf.synth.reference_weekly_demand(n_skus=1)
+    one = df[df["SKU"] == df["SKU"].iloc[0]].sort_values("Date")
+    y = one["Demand"].to_numpy(dtype=np.float64)
+    X = O.exo_variables(list(one["Date"])).astype(np.float64)
+    ours = O.build_tune_and_score_model(one, design="exog_only")["Demand_Fitted"].to_numpy(dtype=np.float64)
+    ytr, Xtr = y[:117], X[:117]
+
+    def nll(theta):
+        b, log_s2 = theta[:3], theta[3]
+        r = ytr - Xtr @ b
+        return 0.5 * (117 * (np.log(2 * np.pi) + log_s2) + r @ r / np.exp(log_s2))
+
+    skl = LinearRegression(fit_intercept=False).fit(Xtr, ytr)
+    assert np.abs(X @ skl.coef_ - ours).max() <= 1e-6 * np.abs(y).max()
+    b0 = skl.coef_
+    s2 = np.mean((ytr - Xtr @ b0) ** 2)
+    f_star = nll(np.r_[b0, np.log(s2)])
+    for start in (np.r_[b0, np.log(s2)], np.r_[b0 * 1.05 + 10.0, np.log(s2) + 0.3]):
+        res = minimize(nll, start, method="Nelder-Mead", options={"xatol": 1e-9, "fatol": 1e-12, "maxiter": 20000,
+                                                                  "maxfev": 40000})
+        assert res.fun >= f_star - 1e-9                                   # nothing beats the closed form
+        assert res.fun <= f_star + 1e-6 and np.abs(X @ res.x[:3] - ours).max() <= 1e-3 * np.abs(y).max()
+
+
 def test_c_restatement_equals_numpy_oracle(oracle_golden):
     """oracle/mmf_oracle_c.c (the multi-core CPU baseline of bench.py) against the NumPy oracle, incl. gaps,
     an empty row and a rank-deficient mask."""
