@@ -50,6 +50,8 @@ def parse():
                          "into every peer's copy over NVLink (default), nccl = one all_gather after the kernel")
     ap.add_argument("--graph", action="store_true",
                     help="replay each step as a CUDA graph (small batches are launch-bound); single GPU only")
+    ap.add_argument("--pitch-floats", type=int, default=0,
+                    help="row pitch of the device-resident y in floats (0 = T rounded up to 4; 32 | pitch = 128-B aligned rows)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-groups", type=int, default=0, help="groups per step of the reference arm (0 = 16 x cores)")
@@ -229,7 +231,8 @@ def run_ours(args):
     K, W = args.steps, max(args.warmup, 3)
 
     # ---- inputs: resident in HBM before the timed region; 4.4 GB per pass >> 126 MB L2
-    y, start = mmf.synth.daily_store_item_demand_torch(n, t, seed=1234 + rank, nan_frac=args.nan_frac, device=dev)
+    y, start = mmf.synth.daily_store_item_demand_torch(n, t, seed=1234 + rank, nan_frac=args.nan_frac, device=dev,
+                                                        ld=args.pitch_floats or None)
     torch.cuda.synchronize()
     # the all-gathered forecast table.  N>1: NVLink symmetric memory so the fit kernel itself can store every
     # forecast row into all ranks' copies (NVLS multicast or P2P); --gather nccl keeps the plain collective.
