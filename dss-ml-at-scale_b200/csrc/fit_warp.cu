@@ -366,6 +366,7 @@ fit_warp_kernel(const DesignView d, const FitArgs a, const int smem_rows) {
           a.rec_rows[atomicAdd(a.rec_count, 1u)] = row0 + s;
         }
         for (int m = lane; m < nm; m += 32) rec.miss_t[m] = scr.miss_t[s][m];   // segment 1 starts at SOLVE_SEG
+        if (lane < ((nm + 3) & ~3) - nm) rec.miss_t[nm + lane] = 0;             // the solve kernel reads whole 8-B groups
 #pragma unroll
         for (int q = 0; q < S; ++q) if (q == s) deferred[q] = true;
         continue;
