@@ -36,7 +36,15 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--series", type=int, default=1_000_000, help="series per GPU (weak scaling)")
+    ap.add_argument("--series", type=int, default=1_000_000,
+                    help="series per GPU (--scaling weak, default) or in total, block-sharded over the ranks (--scaling strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --series per GPU (driver default); strong: --series in total = BASELINE configs[3] as worded "
+                         "(1 M groups over 8 GPUs + one all-gather of the forecast table)")
+    ap.add_argument("--tc-variant", type=int, default=0, choices=[0, 1, 2],
+                    help="tcgen05 kernel instantiation: 0 auto, 1 = 10 stages / 1 staging tile, 2 = 8 stages / 2 staging tiles")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the live ncu DRAM-traffic probe of the dominant kernel")
+    ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--t", type=int, default=1095)
     ap.add_argument("--horizon", type=int, default=28)
     ap.add_argument("--kernel", default="auto", choices=["auto", "warp", "tc"])
@@ -121,17 +129,21 @@ def cpu_port_baseline(y_sample, start, t, h):
     if not os.path.exists(so):
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], capture_output=True)
     if os.path.exists(so):
-        y32 = np.ascontiguousarray(y_sample, dtype=np.float32)
-        _, _, used = O.fit_forecast_packed_c(y32[:1024], X, t, t, h, return_threads=True)        # warm
+        # pages first-touched by the pinned worker thread that later reads them: the same placement on every box
+        # (round 1's sample lived on whichever NUMA node the rank had been bound to and moved 3.3x between boxes)
+        y32 = O.numa_local_sample(np.ascontiguousarray(y_sample, dtype=np.float32))
+        prep = {}
+        out, st, used = O.fit_forecast_packed_c(y32, X, t, t, h, return_threads=True, prepared=prep)   # warm, same placement
         t0 = time.perf_counter()
         done = 0
         while time.perf_counter() - t0 < 12.0:
-            _, _, used = O.fit_forecast_packed_c(y32, X, t, t, h, return_threads=True)
+            O.fit_forecast_packed_c(y32, X, t, t, h, out=out, status=st, prepared=prep)
             done += n_s
         dt = time.perf_counter() - t0
         return {"value": done / dt, "unit": UNIT, "cores": used, "kind": "port",
                 "sample": f"{done} series x {t} days ({done // n_s} passes over {n_s} distinct), C restatement of the oracle "
-                          f"(float64 accumulation, one pass per series, {used} pthreads), {dt:.1f} s"}
+                          f"(float64 accumulation, one pass per series, {used} pthreads pinned one per core, sample pages "
+                          f"first-touched by the thread that reads them), {dt:.1f} s"}
     O.fit_forecast_packed(y_sample[:256], X, t, t, h)                 # warm
     t0 = time.perf_counter()
     done = 0
@@ -209,6 +221,99 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def nvlink_counters(index):
+    """Sum of the NVLink data counters of GPU `index` in bytes (tx, rx), or None: `nvidia-smi nvlink -gt d`."""
+    try:
+        r = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True, timeout=20)
+        tx = rx = 0
+        seen = False
+        for line in r.stdout.splitlines():
+            parts = line.replace(":", " ").split()
+            if "Tx" in parts or "Rx" in parts:
+                val = float(parts[-2])
+                mult = {"KiB": 1024.0, "MiB": 1024.0 ** 2, "GiB": 1024.0 ** 3, "B": 1.0}.get(parts[-1], 1024.0)
+                if "Tx" in parts:
+                    tx += val * mult
+                else:
+                    rx += val * mult
+                seen = True
+        return (tx, rx) if seen else None
+    except Exception:
+        return None
+
+
+TRAFFIC_KERNELS = "fit_tc_kernel|fit_warp_kernel|predict_tc_kernel|solve_rows_kernel"
+
+
+def traffic_child(args):
+    """Child of the live traffic probe (runs under ncu): the same launch as a bench step on the same shape --
+    values do not change the bytes a gap-free pass moves, so the input is a cheap random level + noise."""
+    import torch
+    import mmf
+    torch.cuda.set_device(0)
+    n, t, h = args.series, args.t, args.horizon
+    ld = args.pitch_floats or ((t + 3) & ~3)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    y = (torch.randn((n, ld), generator=g, device="cuda") * 100.0 + 10000.0).round_()[:, :t]
+    if args.nan_frac > 0:
+        y[torch.rand((n, t), generator=g, device="cuda") < args.nan_frac] = float("nan")
+    _, start = mmf.synth.daily_store_item_demand(1, t, seed=0)
+    eng = mmf.ForecastEngine(device=0, kernel=args.kernel, tc_variant=args.tc_variant)
+    _, ps, npred = eng.plan_calendar(start, t, "D", h, args.mode)
+    out = torch.empty((n, (npred + 3) & ~3), device="cuda")[:, :npred] if args.mode == "holdout" else torch.empty((n, h), device="cuda")
+    eng.fit_forecast(y, ps, npred, out=out)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    eng.fit_forecast(y, ps, npred, out=out)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+    eng.close()
+
+
+def live_traffic(args, n, kernel_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel on this run's shape, measured
+    now: `ncu` around a child process that issues the same launch (the bench's own timed steps never run under a
+    profiler).  Returns (bytes or None, note)."""
+    import shutil
+    import tempfile
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None, "ncu not found"
+    log = os.path.join(tempfile.mkdtemp(prefix="mmf_ncu_"), "traffic.csv")
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum", "--clock-control", "none",
+           "--profile-from-start", "off", "-k", f"regex:{TRAFFIC_KERNELS}", "--csv", "--print-units", "base",
+           "--log-file", log, sys.executable, os.path.abspath(__file__), "--traffic-child", "--series", str(n),
+           "--t", str(args.t), "--horizon", str(args.horizon), "--kernel", args.kernel, "--mode", args.mode,
+           "--nan-frac", str(args.nan_frac), "--tc-variant", str(args.tc_variant), "--pitch-floats", str(args.pitch_floats)]
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=420, env=env)
+        if r.returncode != 0 or not os.path.exists(log):
+            return None, f"ncu probe failed (rc {r.returncode}): {(r.stderr or r.stdout)[-200:]!r}"
+        import csv
+        rows = []
+        with open(log) as f:
+            lines = [ln for ln in f if not ln.startswith("==")]
+        for row in csv.DictReader(lines):
+            rows.append(row)
+        per = {}
+        for row in rows:
+            kn = row.get("Kernel Name", "")
+            if kernel_name not in kn:
+                continue
+            m, v = row.get("Metric Name"), float(row.get("Metric Value", "0").replace(",", ""))
+            per.setdefault(row.get("ID"), {})[m] = v
+        if not per:
+            return None, f"no {kernel_name} launch in the ncu log"
+        tot = [d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0) for d in per.values()]
+        return sum(tot) / len(tot), (f"live: ncu dram__bytes_read.sum + dram__bytes_write.sum, {len(tot)} launch(es) of "
+                                     f"{kernel_name} on this run's shape in a child process, this box")
+    except Exception as exc:        # noqa: BLE001 -- the probe must never take the bench down
+        return None, f"ncu probe failed: {exc!r}"
+
+
 # =========================================================================================
 def run_ours(args):
     import numpy as np
@@ -227,7 +332,9 @@ def run_ours(args):
     numa_cpus = mmf.bind_to_gpu_numa(local)             # pinned staging buffers land on the GPU's NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    n, t, h = args.series, args.t, args.horizon
+    t, h = args.t, args.horizon
+    # weak: --series per GPU; strong: --series in total, equal contiguous blocks of ceil(total/world) rows per rank
+    n = args.series if args.scaling == "weak" else -(-args.series // world)
     K, W = args.steps, max(args.warmup, 3)
 
     # ---- inputs: resident in HBM before the timed region; 4.4 GB per pass >> 126 MB L2
@@ -257,7 +364,7 @@ def run_ours(args):
         gather = "nccl-all_gather" if world > 1 else "none"
     mine = table[rank * n:(rank + 1) * n]
 
-    eng = mmf.ForecastEngine(device=local, kernel=args.kernel)
+    eng = mmf.ForecastEngine(device=local, kernel=args.kernel, tc_variant=args.tc_variant)
     # ForecastEngine enqueues on torch's current stream for CUDA tensors, so the CUDA events below see the kernels
     _, ps, npred = eng.plan_calendar(start, t, "D", h, args.mode)
     if args.mode == "holdout":
@@ -310,6 +417,7 @@ def run_ours(args):
         dist.barrier()
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K + 2)]
+    nvl0 = nvlink_counters(local) if (rank == 0 and world > 1) else None
     torch.cuda.profiler.start()          # `ncu --profile-from-start off` captures exactly the timed region
     wall0 = time.time()
     ev[0].record()
@@ -325,6 +433,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
     wall1 = time.time()
+    nvl1 = nvlink_counters(local) if nvl0 is not None else None
     total_ms = ev[0].elapsed_time(ev[1])
     kern_ms = [ev[2 + 2 * i].elapsed_time(ev[3 + 2 * i]) for i in range(K)]
     tt = torch.tensor([total_ms, sum(kern_ms) / K], device=dev, dtype=torch.float64)
@@ -353,7 +462,14 @@ def run_ours(args):
         torch.cuda.synchronize()
         so = torch.tensor([s0.elapsed_time(s1)], device=dev, dtype=torch.float64)
         dist.all_reduce(so, op=dist.ReduceOp.MAX)
+        nvlink = None
+        if nvl0 is not None and nvl1 is not None:       # rank 0's GPU, driver counters around the timed region
+            nvlink = {"tx_bytes_per_step": (nvl1[0] - nvl0[0]) / K, "rx_bytes_per_step": (nvl1[1] - nvl0[1]) / K,
+                      "tx_GBps": (nvl1[0] - nvl0[0]) / (total_ms * 1e-3) / 1e9,
+                      "rx_GBps": (nvl1[1] - nvl0[1]) / (total_ms * 1e-3) / 1e9,
+                      "source": "nvidia-smi nvlink -gt d on rank 0's GPU before / after the timed region"}
         shard_only = {"value": world * n * K / (float(so[0]) * 1e-3), "unit": "series/s", "ms_per_step": float(so[0]) / K,
+                      "nvlink": nvlink,
                       "note": "same K steps, forecasts kept on the fitting rank (no table replication); max over ranks",
                       "replication_bytes_in_per_gpu_per_step": (world - 1) * n * h * 4,
                       "replication_ingress_GBps_per_gpu": (world - 1) * n * h * 4 / (total_ms / K * 1e-3) / 1e9}
@@ -364,28 +480,17 @@ def run_ours(args):
         del ref, loc
 
     # ---- roofline of the dominant kernel (algorithmic bytes: 4*T read + 4*H written per series)
-    def ncu_traffic():
-        """dram__bytes_read.sum + dram__bytes_write.sum per launch of fit_tc_kernel from the committed
-        `ncu --set full` capture (profiles/r01/final_tc_final.txt) -- valid for the workload it was taken on."""
-        if not (kernel_used == "tc" and n == 1_000_000 and t == 1095 and h == 28 and args.mode == "future"
-                and args.nan_frac == 0.0):
-            return None
-        try:
-            with open(os.path.join(ROOT, "profiles", "r01", "final_tc_final.txt")) as f:
-                for line in f:
-                    if line.startswith("traffic (dram read + write) per launch:"):
-                        return float(line.split(":")[1].split()[0]) * 1e9
-        except OSError:
-            pass
-        return None
-
     peak, peak_src = peaks()
     bytes_per_series = 4 * t + 4 * h if args.mode == "future" else 4 * (t - h) + 4 * t
     achieved = n * bytes_per_series / (kern_ms_avg * 1e-3) / 1e9
+    dom_kernel = "fit_tc_kernel" if kernel_used == "tc" else "fit_warp_kernel"
+    traffic, traffic_note = (None, "not probed")
+    if rank == 0 and world == 1 and not args.no_traffic:
+        traffic, traffic_note = live_traffic(args, n, dom_kernel)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(), "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01/final_tc_final.txt)",
+                "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_note,
                 "algorithmic_bytes_per_launch": n * bytes_per_series,
-                "kernel": "fit_tc_kernel" if kernel_used == "tc" else "fit_warp_kernel",
+                "kernel": dom_kernel,
                 "peak_source": peak_src, "bytes_per_series": bytes_per_series,
                 "kernel_ms": kern_ms_avg,
                 "note": "CUDA events around each step's libmmf launches in the timed region, max over ranks"}
@@ -427,10 +532,13 @@ def run_ours(args):
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"{n} (store,item) series x {t} days per GPU, {h}-day horizon, future mode "
-                                       f"(BASELINE configs[3] shape; weak scaling)",
+                "config": {"workload": (f"{n} (store,item) series x {t} days per GPU, {h}-day horizon, {args.mode} mode "
+                                        f"(BASELINE configs[3] shape; weak scaling)" if args.scaling == "weak" else
+                                        f"{world * n} (store,item) series x {t} days in total, {n} per GPU (block-sharded), "
+                                        f"{h}-day horizon, {args.mode} mode (BASELINE configs[3] as worded; strong scaling)"),
+                           "tc_variant": args.tc_variant,
                            "series_per_gpu": n, "t": t, "horizon": h, "nan_frac": args.nan_frac, "mode": args.mode,
                            "kernel": kernel_used,
                            "l2": (f"inputs {in_bytes / 1e9:.2f} GB per step per GPU > 126 MB L2" if n_rot == 1 else
@@ -450,7 +558,9 @@ def run_ours(args):
 
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
+    if a.traffic_child:
+        traffic_child(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)

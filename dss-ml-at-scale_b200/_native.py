@@ -9,7 +9,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmmf.so")
+# MMF_LIB: load another build of the same ABI (tests use it for the negative-control build without the lo*A_hi
+# tensor-core term); the default is the in-tree product library
+LIB_PATH = os.environ.get("MMF_LIB") or os.path.join(_HERE, "libmmf.so")
 
 MMF_P = 16
 KERNEL_AUTO, KERNEL_WARP, KERNEL_TC = 0, 1, 2
@@ -19,7 +21,7 @@ KERNELS = {"auto": KERNEL_AUTO, "warp": KERNEL_WARP, "tc": KERNEL_TC}
 # every symbol include/mmf.h declares (tests/test_abi.py checks the library exports them all)
 EXPORTS = (
     "mmf_version", "mmf_last_error", "mmf_device_count", "mmf_create", "mmf_destroy",
-    "mmf_set_stream", "mmf_synchronize", "mmf_plan_design", "mmf_get_whitening",
+    "mmf_set_stream", "mmf_synchronize", "mmf_plan_design", "mmf_pin_scratch", "mmf_get_whitening",
     "mmf_fit_forecast_f32", "mmf_fit_forecast_bcast_f32", "mmf_fit_select_forecast_f32", "mmf_pack_hash_utf8", "mmf_pack_hash_i32",
     "mmf_pack_group_codes", "mmf_pack_verify_utf8", "mmf_pack_verify_i32", "mmf_pack_minmax", "mmf_pack_scatter_f32", "mmf_alloc_pinned", "mmf_free_pinned",
     "mmf_host_register", "mmf_host_unregister",
@@ -31,7 +33,7 @@ class MmfConfig(C.Structure):
         ("device", C.c_int32),
         ("kernel", C.c_int32),
         ("assume_finite", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("tc_variant", C.c_int32),
         ("chunk_series", C.c_int64),
         ("stream", C.c_void_p),
     ]
@@ -78,6 +80,7 @@ def load() -> C.CDLL:
     lib.mmf_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     lib.mmf_synchronize.argtypes = [C.c_void_p]
     lib.mmf_plan_design.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    lib.mmf_pin_scratch.argtypes = [C.c_void_p, C.c_int32]
     lib.mmf_get_whitening.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.mmf_fit_forecast_f32.argtypes = [
         C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,

@@ -27,15 +27,14 @@ namespace {
 
 using namespace sm100;
 
-#ifndef MMF_TC_STAGES
-#define MMF_TC_STAGES 10
-#endif
 #ifndef MMF_TC_ASLOTS
 #define MMF_TC_ASLOTS 2
 #endif
 constexpr int TILE_M = 128;            // series per tile == TMEM lanes
 constexpr int KC = 32;                 // time steps per stage == one 128-B swizzle row
-constexpr int STAGES = MMF_TC_STAGES;  // shared-memory ring (20 KB per stage)
+// The shared-memory ring (20 KB per stage) and the number of forecast staging tiles are template parameters of the
+// kernel: <10 stages, 1 staging tile> for a single destination, <8, 2> when the tile also goes to peer GPUs (the
+// second staging tile lets tile k+1 be assembled while the NVLink stores of tile k are still reading tile k's).
 constexpr int NGROUPS = 2;             // transform groups (alternate chunks)
 constexpr int ASLOTS = MMF_TC_ASLOTS;  // TMEM A-operand slots per transform group
 constexpr int MAX_PRED = 64;           // forecast rows the epilogue supports
@@ -49,19 +48,21 @@ constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t ACC_COL0 = 0;                    // 2 accumulator buffers x 32 columns
 constexpr uint32_t ASLOT_COL0 = 64;                 // group g, slot j: hi at 64 + (g*ASLOTS + j)*64, lo 32 further
 static_assert(64 + NGROUPS * ASLOTS * 64 <= 512, "TMEM holds 512 columns");
-static_assert(STAGES % NGROUPS == 0, "each transform group must always see the same stages");
 
-struct SmemLayout {
+template <int STAGES, int OBUF>
+struct SmemLayoutT {
+  static_assert(STAGES % NGROUPS == 0, "each transform group must always see the same stages");
   // offsets from the 1024-aligned base
   static constexpr int y = 0;
   static constexpr int at = y + STAGES * Y_STAGE_BYTES;
   static constexpr int apred = at + STAGES * AT_STAGE_BYTES;
   static constexpr int ostage = apred + MAX_PRED * P * 4;            // forecast tile staged for the bulk stores
-  static constexpr int nm = ostage + TILE_M * BULK_MAX_PRED * 4;     // per-row missing counts: [NM_RING][2 groups][128] u16
+  static constexpr int nm = ostage + OBUF * TILE_M * BULK_MAX_PRED * 4;   // per-row missing counts: [NM_RING][2 groups][128] u16
   static constexpr int bars = nm + NM_RING * NGROUPS * TILE_M * 2;
   static constexpr int n_bars = 2 * STAGES + 2 * NGROUPS * ASLOTS + 4 + NM_RING;
   static constexpr int tmem_ptr = bars + n_bars * 8;
   static constexpr int total = tmem_ptr + 16;
+  static_assert(total + 1024 <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
 };
 
 __device__ __forceinline__ float dot16(const float* __restrict__ arow, const float (&g)[P], float s) {
@@ -92,9 +93,11 @@ __device__ __forceinline__ float centring_constant(const float* __restrict__ yro
   return c;
 }
 
+template <int STAGES, int OBUF>
 __global__ void __launch_bounds__(THREADS, 1)
 fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const FitArgs a,
               uint32_t* __restrict__ pending_count, const int n_tiles, const int n_chunks) {
+  using SmemLayout = SmemLayoutT<STAGES, OBUF>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   const uint32_t sbase = smem_u32(smem);
@@ -206,7 +209,9 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
         for (int k = 0; k < KC / 8; ++k) {
           const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(k * 2);       // +32 B (16-B units)
           umma_tf32_ts_elect(d_acc, a_hi + k * 8, bdesc, IDESC_N32, (ch | k) != 0 ? 1u : 0u);
+#ifndef MMF_TC_NO_LO_TERM      // negative-control build (tests): without lo*A_hi the path is tf32-grade and must FAIL parity
           umma_tf32_ts_elect(d_acc, a_lo + k * 8, bdesc, IDESC_N16, 1u);
+#endif
         }
         umma_commit_elect(bar_aempty(grp, aslot));
         umma_commit_elect(bar_empty(stage));
@@ -368,7 +373,9 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
         const bool has1 = n_chunks >= 2 || ((lt * n_chunks) & 1) == 1;
         const unsigned f0 = has0 ? nmrow[0] : 0u, f1 = has1 ? nmrow[TILE_M] : 0u;
         nm0 = f0 & 0x7fff; nm1 = f1 & 0x7fff;
-        general = ((f0 | f1) & 0x8000u) != 0u || nm0 > SOLVE_SEG || nm1 > SOLVE_SEG;
+        // mostly-missing rows: the downdate I - sum a a^T cancels catastrophically; fit_warp builds their Gram
+        // directly over the observed rows (same rule as fit_warp.cu)
+        general = ((f0 | f1) & 0x8000u) != 0u || nm0 > SOLVE_SEG || nm1 > SOLVE_SEG || 2 * (nm0 + nm1) > d.t_fit;
         if (general) c = 0.f;
       }
       tmem_wait_ld();
@@ -400,13 +407,16 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
           rec.c = c;
           rec.nm[0] = static_cast<uint16_t>(nm0);
           rec.nm[1] = static_cast<uint16_t>(nm1);
-          a.rec_rows[base + __popc(dm & ((1u << lane) - 1u))] = row;
+          const unsigned slot = base + __popc(dm & ((1u << lane) - 1u));
+          if (slot < a.rec_cap) a.rec_rows[slot] = row;
         }
       }
       if (bulk) {
-        if (warp == WARP_EPI0) bulk_wait_read_elect();  // last tile's bulk stores no longer read the staging tile
+        // staging tile lt % OBUF: the bulk stores that read it last (tile lt - OBUF) must have drained it
+        const int ob = OBUF > 1 ? (lt % OBUF) : 0;
+        if (warp == WARP_EPI0) { if (OBUF > 1) bulk_wait_read1_elect(); else bulk_wait_read_elect(); }
         named_bar_sync(1, 128);
-        float* __restrict__ srow = s_ostage + r * a.n_pred;
+        float* __restrict__ srow = s_ostage + ob * (TILE_M * BULK_MAX_PRED) + r * a.n_pred;
         for (int k = 0; k < a.n_pred; k += 4) {          // PENDING rows stage garbage; the fix-up pass rewrites them
           float o[4];
 #pragma unroll
@@ -419,9 +429,16 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
           const int64_t rows_here = (a.n - (int64_t)tile * TILE_M) < TILE_M ? (a.n - (int64_t)tile * TILE_M) : TILE_M;
           const uint32_t bytes = static_cast<uint32_t>(rows_here) * a.n_pred * 4u;
           const int64_t off = (int64_t)tile * TILE_M * a.n_pred;
-          bulk_store_elect(reinterpret_cast<uint64_t>(a.out + off), s_ostage_u32, bytes);
-          for (int i = 0; i + 1 < a.n_out; ++i)
-            bulk_store_elect(reinterpret_cast<uint64_t>(a.out_more[i] + off), s_ostage_u32, bytes);
+          const uint32_t src = s_ostage_u32 + static_cast<uint32_t>(ob) * (TILE_M * BULK_MAX_PRED * 4);
+          bulk_store_elect(reinterpret_cast<uint64_t>(a.out + off), src, bytes);
+          // peers: every tile starts at another peer, so at any moment this GPU's 148 store queues target all
+          // peers evenly instead of all hammering the first one in the list (NVLink ingress hot spot)
+          const int n_peer = a.n_out - 1;
+          int j = n_peer > 1 ? tile % n_peer : 0;
+          for (int i = 0; i < n_peer; ++i) {
+            bulk_store_elect(reinterpret_cast<uint64_t>(a.out_more[j] + off), src, bytes);
+            if (++j == n_peer) j = 0;
+          }
           bulk_commit_elect();
         }
       } else if (live && !pend && !defer && !a.skip_pred) {
@@ -486,17 +503,26 @@ bool fit_tc_supported(const DesignView& d, const FitArgs& a, const char** why) {
   return w == nullptr;
 }
 
+template <int STAGES, int OBUF>
+static cudaError_t launch_variant(const DesignView& d, const FitArgs& a, const TcLaunch& tl, uint32_t* pending_count,
+                                  int sm_count, cudaStream_t s, int n_tiles, int n_chunks) {
+  const size_t smem = SmemLayoutT<STAGES, OBUF>::total + 1024;
+  cudaError_t e = cudaFuncSetAttribute(fit_tc_kernel<STAGES, OBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int grid = n_tiles < sm_count ? n_tiles : sm_count;
+  fit_tc_kernel<STAGES, OBUF><<<grid, THREADS, smem, s>>>(tl, d, a, pending_count, n_tiles, n_chunks);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_fit_tc(const DesignView& d, const FitArgs& a, const TcLaunch& tl, uint32_t* pending_count,
-                          int sm_count, cudaStream_t s) {
+                          int sm_count, cudaStream_t s, int variant) {
   if (a.n <= 0) return cudaSuccess;
   const int n_tiles = (int)((a.n + TILE_M - 1) / TILE_M);
   const int n_chunks = d.t_pad / KC;
-  const size_t smem = SmemLayout::total + 1024;
-  cudaError_t e = cudaFuncSetAttribute(fit_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  const int grid = n_tiles < sm_count ? n_tiles : sm_count;
-  fit_tc_kernel<<<grid, THREADS, smem, s>>>(tl, d, a, pending_count, n_tiles, n_chunks);
-  return cudaGetLastError();
+  // variant 0 = automatic: two staging tiles as soon as a tile has more than one destination
+  const bool two = variant == 2 || (variant == 0 && (a.n_out > 1 || a.out_multimem == 2));
+  return two ? launch_variant<8, 2>(d, a, tl, pending_count, sm_count, s, n_tiles, n_chunks)
+             : launch_variant<10, 1>(d, a, tl, pending_count, sm_count, s, n_tiles, n_chunks);
 }
 
 }  // namespace mmf

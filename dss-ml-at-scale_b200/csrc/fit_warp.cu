@@ -1,16 +1,16 @@
 // fit_warp.cu -- warp-per-series-group fit + forecast on CUDA cores (general path).
 //
-// One warp owns S = 4 consecutive series (four (Product,SKU) groups of the reference fan-out,
+// One warp owns S = MMF_WARP_S (2) consecutive series ((Product,SKU) groups of the reference fan-out,
 // group_apply/02_Fine_Grained_Demand_Forecasting.py:523-528) and does what the reference UDF does
 // for each (02:435-494) in the whitened calendar basis:
 //   b   = sum_{t observed} a_t (y_t - c)     lanes stride over t (coalesced 128-B row segments); one
-//                                            LDS.128 x4 design-row fetch feeds 4 series = 64 FMAs
+//                                            LDS.128 x4 design-row fetch feeds S series = 16*S FMAs
 //   fully observed series : G_i = I, gamma = b
 //   series with gaps      : second pass over the (L2-hot) row builds D = sum_{missing} a_t a_t^T
 //                           warp-cooperatively (or the Gram over the observed rows when most are
 //                           missing), then an in-order Cholesky of G_i in shared memory with pivot
 //                           dropping and two triangular solves -- one warp per series
-//   yhat_t = c + a_t . gamma                  for the requested rows, again 4 series per design row
+//   yhat_t = c + a_t . gamma                  for the requested rows, again S series per design row
 // It handles everything (NaN masks, any leading dimension, any number of prediction rows: the
 // reference's "Demand_Fitted for every date" contract, 02:484-494) and is also the masked fix-up
 // pass behind the tcgen05 kernel.  Bound: HBM; see DESIGN.md section 4.
@@ -363,7 +363,8 @@ fit_warp_kernel(const DesignView d, const FitArgs a, const int smem_rows) {
           rec.c = cs;
           rec.nm[0] = (uint16_t)(nm < SOLVE_SEG ? nm : SOLVE_SEG);
           rec.nm[1] = (uint16_t)(nm < SOLVE_SEG ? 0 : nm - SOLVE_SEG);
-          a.rec_rows[atomicAdd(a.rec_count, 1u)] = row0 + s;
+          const unsigned slot = atomicAdd(a.rec_count, 1u);
+          if (slot < a.rec_cap) a.rec_rows[slot] = row0 + s;
         }
         for (int m = lane; m < nm; m += 32) rec.miss_t[m] = scr.miss_t[s][m];   // segment 1 starts at SOLVE_SEG
         if (lane < ((nm + 3) & ~3) - nm) rec.miss_t[nm + lane] = 0;             // the solve kernel reads whole 8-B groups

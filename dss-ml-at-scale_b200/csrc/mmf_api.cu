@@ -104,8 +104,13 @@ struct mmf_ctx {
   bool own_stream = false;
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
-  uint32_t* d_pending = nullptr;       // 2 ping-pong sets of {rows left PENDING, solve records queued}
-  int counter_set = 0;
+  uint32_t* d_pending = nullptr;       // 3 sets of {rows left PENDING, solve records queued}: 0/1 ping-pong between
+                                       // eager calls, 2 belongs to captured CUDA graphs (zeroed by a node of the graph)
+  int counter_set = 0;                 // set the next eager call uses
+  bool set_clean[2] = {true, true};    // the set is known to be zero (cudaMemset at create, or zeroed by the previous
+                                       // eager call's tcgen05 kernel); anything else makes the call memset its set
+  int last_set = 0;                    // set the last enqueued call used (stats read n_pending from it)
+  int pinned = 0;                      // > 0: a captured CUDA graph holds pointers into the scratch below and into the plan
   SolveRec* d_recs = nullptr;          // deferred masked series (grown on demand, capped)
   size_t recs_cap_bytes = 0;
   int64_t* d_rec_rows = nullptr;
@@ -129,8 +134,13 @@ void free_plan(Plan& p) {
   p = Plan{};
 }
 
+// Scratch that a captured CUDA graph points into must not move: while ctx->pinned > 0 a reallocation is refused.
+thread_local const mmf_ctx* g_grow_ctx = nullptr;
 int grow(void** ptr, size_t* cap, size_t need) {
   if (*cap >= need) return MMF_OK;
+  if (g_grow_ctx && g_grow_ctx->pinned > 0)
+    return fail(MMF_E_UNSUPPORTED, "a captured CUDA graph holds this context's scratch (%zu B) and the call needs %zu B: "
+                "release the graph (mmf_pin_scratch(ctx, -1)) or use another context for larger batches", *cap, need);
   if (*ptr) cudaFree(*ptr);
   *ptr = nullptr; *cap = 0;
   cudaError_t e = cudaMalloc(ptr, need);
@@ -198,28 +208,26 @@ int run_device(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, int32_t pr
     a.rec_rows = ctx->d_rec_rows;
     a.rec_cap = (uint32_t)cap;
   }
-  // counters: this call uses set `cs`; the tcgen05 kernel zeroes the other set for the next call, so the common
-  // path has no memset node (the warp-only path still clears its set explicitly)
-  const int cs = ctx->counter_set;
-  uint32_t* counters = ctx->d_pending + 2 * cs;
-  ctx->counter_set ^= 1;
-  if (may_mask) a.rec_count = counters + 1;
-  // Under stream capture the launches become a graph that is replayed with THIS counter set every time, so the
-  // set cannot rely on the previous call having zeroed it: the graph gets its own memset node.
+  // counters: an eager call uses ping-pong set `cs`; its tcgen05 kernel zeroes the other set for the next eager
+  // call, so the common path has no memset node.  A set that is not known to be zero (first use after a warp-only
+  // call, after an error, ...) is cleared explicitly.  Under stream capture the launches become a graph that is
+  // replayed any number of times, interleaved with eager calls: it gets set 2, zeroed by a memset node of its own,
+  // and leaves the ping-pong state alone.
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   CU_TRY(cudaStreamIsCapturing(s, &cap));
-  if (kernel == MMF_KERNEL_TC) {
-    a.zero_next = ctx->d_pending + 2 * (cs ^ 1);
-    if (cap != cudaStreamCaptureStatusNone) CU_TRY(cudaMemsetAsync(counters, 0, 2 * sizeof(uint32_t), s));
-  } else {
-    CU_TRY(cudaMemsetAsync(ctx->d_pending, 0, 4 * sizeof(uint32_t), s));
-  }
+  const bool capturing = cap != cudaStreamCaptureStatusNone;
+  const int cs = capturing ? 2 : ctx->counter_set;
+  uint32_t* counters = ctx->d_pending + 2 * cs;
+  if (may_mask) a.rec_count = counters + 1;
+  if (capturing || !ctx->set_clean[cs]) CU_TRY(cudaMemsetAsync(counters, 0, 2 * sizeof(uint32_t), s));
+  if (!capturing) ctx->set_clean[cs] = false;             // dirty from here on, whatever happens below
+  if (kernel == MMF_KERNEL_TC && !capturing) a.zero_next = ctx->d_pending + 2 * (cs ^ 1);
   if (kernel == MMF_KERNEL_TC) {
     TcLaunch tl;
     int rc = encode_2d(tl.tmap_y, y, (uint64_t)d.t_fit, (uint64_t)n, (uint64_t)ld_y * 4, 32, 128);
     if (rc != MMF_OK) return rc;
     memcpy(tl.tmap_at, ctx->plan.tmap_at, 128);
-    CU_TRY(launch_fit_tc(d, a, tl, counters, ctx->sm_count, s));
+    CU_TRY(launch_fit_tc(d, a, tl, counters, ctx->sm_count, s, ctx->cfg.tc_variant));
     ++*launches;
     if (may_mask) {
       FitArgs m = a;
@@ -251,8 +259,18 @@ int run_device(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, int32_t pr
     ++*launches;
   }
   *kernel_used = kernel;
+  ctx->last_set = cs;
+  if (!capturing) {                                       // toggle only once every launch of the call is enqueued
+    ctx->set_clean[cs ^ 1] = (kernel == MMF_KERNEL_TC);   // zeroed by this call's tcgen05 kernel
+    ctx->counter_set = cs ^ 1;
+  }
   return MMF_OK;
 }
+
+struct GrowScope {                                        // entry points that may reallocate scratch name their ctx
+  explicit GrowScope(const mmf_ctx* c) { g_grow_ctx = c; }
+  ~GrowScope() { g_grow_ctx = nullptr; }
+};
 
 }  // namespace
 
@@ -317,8 +335,8 @@ int mmf_create(const mmf_config* cfg, mmf_ctx** out) {
     cudaEventCreateWithFlags(&ctx->st[i].ev_comp, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->st[i].ev_d2h, cudaEventDisableTiming);
   }
-  if ((e = cudaMalloc(&ctx->d_pending, 4 * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
-  cudaMemset(ctx->d_pending, 0, 4 * sizeof(uint32_t));
+  if ((e = cudaMalloc(&ctx->d_pending, 6 * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
+  cudaMemset(ctx->d_pending, 0, 6 * sizeof(uint32_t));
   *out = ctx;
   return MMF_OK;
 }
@@ -379,6 +397,9 @@ int mmf_plan_design(mmf_ctx* ctx, const double* X, int32_t n_rows, int32_t p, in
   if (has_constant)
     for (int32_t t = 0; t < n_rows; ++t)
       if (X[(int64_t)t * p] != 1.0) return fail(MMF_E_INVALID, "has_constant=1 but X[%d,0] != 1", t);
+  if (ctx->pinned > 0)
+    return fail(MMF_E_UNSUPPORTED, "a captured CUDA graph references the current plan: release it (mmf_pin_scratch(ctx, -1)) "
+                "before planning another design, or plan it on another context");
   CU_TRY(cudaSetDevice(ctx->device));
   CU_TRY(cudaStreamSynchronize(ctx->stream));
   free_plan(ctx->plan);
@@ -487,6 +508,13 @@ int mmf_plan_design(mmf_ctx* ctx, const double* X, int32_t n_rows, int32_t p, in
   return MMF_OK;
 }
 
+int mmf_pin_scratch(mmf_ctx* ctx, int32_t delta) {
+  if (!ctx) return fail(MMF_E_INVALID, "ctx is NULL");
+  if (ctx->pinned + delta < 0) return fail(MMF_E_INVALID, "unbalanced mmf_pin_scratch");
+  ctx->pinned += delta;
+  return MMF_OK;
+}
+
 int mmf_get_whitening(mmf_ctx* ctx, double* W, int32_t* kept) {
   if (!ctx) return fail(MMF_E_INVALID, "ctx is NULL");
   if (!ctx->plan.valid) return fail(MMF_E_NOPLAN, "no design planned");
@@ -498,6 +526,7 @@ int mmf_get_whitening(mmf_ctx* ctx, double* W, int32_t* kept) {
 int mmf_fit_forecast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, int32_t pred_start, int32_t n_pred,
                          float* out_pred, int64_t ld_out, float* out_beta, int32_t* out_status, mmf_stats* stats) {
   if (!ctx) return fail(MMF_E_INVALID, "ctx is NULL");
+  GrowScope grow_scope(ctx);
   if (!ctx->plan.valid) return fail(MMF_E_NOPLAN, "mmf_plan_design has not been called");
   const Plan& pl = ctx->plan;
   if (n < 0) return fail(MMF_E_INVALID, "n < 0");
@@ -535,7 +564,7 @@ int mmf_fit_forecast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, 
       CU_TRY(cudaEventElapsedTime(&stats->kernel_ms, ctx->ev_k0, ctx->ev_k1));
       stats->total_ms = stats->kernel_ms;
       uint32_t pend = 0;
-      CU_TRY(cudaMemcpy(&pend, ctx->d_pending + 2 * (ctx->counter_set ^ 1), sizeof(pend), cudaMemcpyDeviceToHost));
+      CU_TRY(cudaMemcpy(&pend, ctx->d_pending + 2 * ctx->last_set, sizeof(pend), cudaMemcpyDeviceToHost));
       stats->n_pending = (kernel_used == MMF_KERNEL_TC) ? pend : 0;
     }
   } else {
@@ -564,8 +593,10 @@ int mmf_fit_forecast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, 
       if (y_dev) { yk = y + off * ld_y; ldk = ld_y; }
       else {
         if (it >= NBUF) CU_TRY(cudaStreamWaitEvent(ctx->s_h2d, s.ev_comp, 0));     // staging buffer free again
-        if (ld_y == pitch)        // already pitched on the host: one contiguous copy (pad columns ride along)
-          CU_TRY(cudaMemcpyAsync(s.d_y, y + off * ld_y, (size_t)m * pitch * 4, cudaMemcpyHostToDevice, ctx->s_h2d));
+        if (ld_y == pitch)        // already pitched on the host: one contiguous copy (pad columns ride along, except
+                                  // behind the caller's very last row, which may be the end of its buffer)
+          CU_TRY(cudaMemcpyAsync(s.d_y, y + off * ld_y, ((size_t)(m - 1) * pitch + (size_t)pl.t_fit) * 4,
+                                 cudaMemcpyHostToDevice, ctx->s_h2d));
         else
           CU_TRY(cudaMemcpy2DAsync(s.d_y, (size_t)pitch * 4, y + off * ld_y, (size_t)ld_y * 4, (size_t)pl.t_fit * 4,
                                    (size_t)m, cudaMemcpyHostToDevice, ctx->s_h2d));
@@ -628,6 +659,7 @@ int mmf_fit_forecast_bcast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t 
                                int32_t n_pred, const uint64_t* out_ptrs, int32_t n_out, int32_t multimem,
                                int64_t ld_out, float* out_beta, int32_t* out_status) {
   if (!ctx) return fail(MMF_E_INVALID, "ctx is NULL");
+  GrowScope grow_scope(ctx);
   if (!ctx->plan.valid) return fail(MMF_E_NOPLAN, "mmf_plan_design has not been called");
   const Plan& pl = ctx->plan;
   if (n < 0 || (n > 0 && (!y || !out_ptrs))) return fail(MMF_E_INVALID, "bad y / out_ptrs / n");
@@ -660,6 +692,7 @@ int mmf_fit_select_forecast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t
                                 float* out_pred, int64_t ld_out, int32_t* out_choice, float* out_mse,
                                 int32_t* out_status) {
   if (!ctx) return fail(MMF_E_INVALID, "ctx is NULL");
+  GrowScope grow_scope(ctx);
   if (!ctx->plan.valid) return fail(MMF_E_NOPLAN, "mmf_plan_design has not been called");
   const Plan& pl = ctx->plan;
   if (n < 0 || (n > 0 && (!y || !out_pred))) return fail(MMF_E_INVALID, "bad y / out_pred / n");
@@ -668,6 +701,9 @@ int mmf_fit_select_forecast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t
     if (candidates[i] < 1 || candidates[i] > P || (i > 0 && candidates[i] <= candidates[i - 1]))
       return fail(MMF_E_INVALID, "candidates must be ascending column counts in [1,%d]", P);
   if (n_hold < 1 || pl.t_fit + n_hold > pl.n_rows) return fail(MMF_E_INVALID, "held-out rows exceed the planned design");
+  if (n_hold > MMF_SELECT_MAX_HOLD)
+    return fail(MMF_E_UNSUPPORTED, "n_hold=%d: select_kernel stages the held-out design rows in shared memory, at most %d",
+                n_hold, MMF_SELECT_MAX_HOLD);
   if (ld_y < pl.t_fit + n_hold) return fail(MMF_E_INVALID, "y must hold the fit rows and the held-out rows");
   if (n_pred < 1 || pred_start < 0 || (int64_t)pred_start + n_pred > pl.n_rows)
     return fail(MMF_E_INVALID, "prediction rows outside the planned design");
@@ -718,6 +754,7 @@ int mmf_pack_group_codes(mmf_ctx* ctx, const uint64_t* hash, int64_t n, int32_t*
   if (n > 0x7fffffff) return fail(MMF_E_UNSUPPORTED, "more than 2^31-1 rows in one pack call");
   size_t need = 0;
   CU_TRY(pack_group_codes_scratch_bytes(n, &need));
+  GrowScope grow_scope(ctx);
   if (int rc = grow(&ctx->d_pack_scratch, &ctx->pack_scratch_cap, need)) return rc;
   CU_TRY(pack_group_codes(hash, n, gid, first_row, n_groups, ctx->d_pack_scratch, ctx->sm_count, ctx->stream));
   return MMF_OK;

@@ -95,8 +95,9 @@ struct TcLaunch {
   alignas(64) unsigned char tmap_y[128];
   alignas(64) unsigned char tmap_at[128];
 };
+// variant: 0 = automatic, 1 = <10 smem stages, 1 forecast staging tile>, 2 = <8 stages, 2 staging tiles>
 cudaError_t launch_fit_tc(const DesignView& d, const FitArgs& a, const TcLaunch& tl,
-                          uint32_t* pending_count, int sm_count, cudaStream_t s);
+                          uint32_t* pending_count, int sm_count, cudaStream_t s, int variant = 0);
 bool fit_tc_supported(const DesignView& d, const FitArgs& a, const char** why);
 
 // per-series model selection by hold-out MSE over nested whitened designs (select.cu)

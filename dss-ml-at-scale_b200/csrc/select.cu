@@ -85,7 +85,12 @@ cudaError_t launch_select(const DesignView& d, const FitArgs& a, const SelectArg
   const int64_t want = (a.n + THREADS - 1) / THREADS;
   const int64_t cap = (int64_t)sm_count * 16;
   const unsigned grid = (unsigned)(want < cap ? want : cap);
-  select_kernel<<<grid, THREADS, (size_t)sel.n_hold * P * sizeof(float), s>>>(d, a, sel);
+  const size_t smem = (size_t)sel.n_hold * P * sizeof(float);       // <= MMF_SELECT_MAX_HOLD * 64 B (validated at the ABI)
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  select_kernel<<<grid, THREADS, smem, s>>>(d, a, sel);
   return cudaGetLastError();
 }
 

@@ -142,13 +142,14 @@ class ForecastEngine:
     """One library context: streams, staging buffers, the planned calendar design."""
 
     def __init__(self, device: int | None = None, kernel: str = "auto", assume_finite: bool = False,
-                 chunk_series: int = 0, stream: int | None = None):
+                 chunk_series: int = 0, stream: int | None = None, tc_variant: int = 0):
         self._lib = N.load()
         cfg = N.MmfConfig()
         cfg.device = -1 if device is None else int(device)
         cfg.kernel = N.KERNELS[kernel]
         cfg.assume_finite = 1 if assume_finite else 0
         cfg.chunk_series = int(chunk_series)
+        cfg.tc_variant = int(tc_variant)
         cfg.stream = stream
         h = C.c_void_p()
         N.check(self._lib.mmf_create(C.byref(cfg), C.byref(h)))
@@ -278,7 +279,13 @@ class ForecastEngine:
         """Record one device-resident ``fit_forecast`` call as a CUDA graph.  Small batches are launch-bound (three
         kernel launches plus the Python/ctypes hop cost more than the kernels themselves): ``graph.replay()``
         re-runs the whole fit on whatever ``y`` holds at that time and overwrites ``out`` / ``status``.
-        Returns ``(graph, out)``.  torch provides the graph object; every node in it is a libmmf kernel."""
+        Returns ``(graph, out)``; ``graph`` is a :class:`CapturedFit`.  torch provides the graph object; every node
+        in it is a libmmf kernel (plus one 8-B memset of the graph's own work counters).
+
+        Lifetime: the graph holds raw pointers to this engine's scratch and planned design.  While the returned
+        object is alive the engine is *pinned*: planning another calendar or a call that needs more scratch (a
+        larger batch) raises ``MmfError`` (MMF_E_UNSUPPORTED) instead of freeing memory under the graph.
+        ``graph.close()`` (or dropping it) unpins."""
         import torch
         if not (_is_torch(y) and y.is_cuda):
             raise ValueError("capture() needs a CUDA tensor")
@@ -293,7 +300,7 @@ class ForecastEngine:
         with torch.cuda.graph(graph):
             self.fit_forecast(y, pred_start, n_pred, out=out, status=status)
         self.set_stream(torch.cuda.current_stream(y.device).cuda_stream)
-        return graph, out
+        return CapturedFit(self, graph, (y, out, status)), out
 
     def fit_select_forecast(self, y, n_hold: int, candidates=(1, 3, 9, 13, 16), pred_start: int = 0,
                             n_pred: int | None = None):
@@ -335,6 +342,32 @@ class ForecastEngine:
         sp = _describe(status, "status")[0] if status is not None else None
         N.check(self._lib.mmf_fit_forecast_bcast_f32(self._h, yp, n, ld_y, int(pred_start), int(n_pred), ptrs,
                                                      len(out_ptrs), int(multimem), int(ld_out), None, sp))
+
+
+class CapturedFit:
+    """A captured fit (``ForecastEngine.capture``): ``replay()`` re-runs it; the engine's scratch and plan stay
+    pinned (``mmf_pin_scratch``) until ``close()`` / garbage collection."""
+
+    def __init__(self, engine: ForecastEngine, graph, keep):
+        self._graph, self._keep = graph, keep        # the graph's buffers must outlive it
+        lib, h = engine._lib, engine._h
+        N.check(lib.mmf_pin_scratch(h, 1))
+        self._unpin = weakref.finalize(self, CapturedFit._release, lib, h, engine._finalizer)
+
+    @staticmethod
+    def _release(lib, h, engine_finalizer):
+        if engine_finalizer.alive:                   # the context may already be gone at interpreter shutdown
+            lib.mmf_pin_scratch(h, -1)
+
+    def replay(self) -> None:
+        if self._graph is None:
+            raise RuntimeError("this captured fit has been closed")
+        self._graph.replay()
+
+    def close(self) -> None:
+        self._graph = None
+        if self._unpin.alive:
+            self._unpin()
 
 
 def bind_to_gpu_numa(device: int = 0):

@@ -126,8 +126,11 @@ class SymmetricTable:
         self.multimem = {"p2p": 0, "multicast": 1, "multicast-bulk": 2}[mode]
         if self.multimem:
             self.out_ptrs = [mc + slice_bytes]
-        else:                                             # own copy first, then the peers' (P2P stores)
-            order = [self.rank] + [r for r in range(self.world) if r != self.rank]
+        else:
+            # own copy first, then the peers' (P2P stores) starting at rank+1: no two ranks walk the peers in the same
+            # order, so no GPU's NVLink ingress is every sender's first target (the kernel additionally starts
+            # each tile at a different peer)
+            order = [self.rank] + [(self.rank + k) % self.world for k in range(1, self.world)]
             self.out_ptrs = [int(self.handle.buffer_ptrs[r]) + slice_bytes for r in order]
 
     def barrier(self):

@@ -35,6 +35,7 @@ extern "C" {
 #define MMF_P 16                 /* design columns (zero-pad narrower designs) */
 #define MMF_PIVOT_TOL 1e-3f      /* per-series relative Cholesky pivot threshold */
 #define MMF_CAL_TOL 1e-10        /* aliasing threshold on the float64 calendar Gram */
+#define MMF_SELECT_MAX_HOLD 3500 /* held-out rows mmf_fit_select_forecast_f32 accepts (64 B of shared memory each) */
 
 /* return codes */
 #define MMF_OK 0
@@ -61,7 +62,8 @@ typedef struct mmf_config {
   int32_t device;          /* CUDA device ordinal, -1 = current device */
   int32_t kernel;          /* MMF_KERNEL_* */
   int32_t assume_finite;   /* 1: caller guarantees y has no NaN/Inf, skip the masked fix-up pass */
-  int32_t reserved0;
+  int32_t tc_variant;      /* tuning: 0 = automatic; 1 / 2 force the <10-stage, 1 staging tile> / <8-stage, 2 staging
+                              tiles> instantiation of the tcgen05 kernel (same results) */
   int64_t chunk_series;    /* host-buffer path: series per pipelined chunk (0 = library default) */
   void*   stream;          /* cudaStream_t to enqueue on (NULL = library-owned stream) */
 } mmf_config;
@@ -97,6 +99,14 @@ int mmf_synchronize(mmf_ctx* ctx);
  * (02:343-358) and hands to SARIMAX as exog= (02:441-449, 472-480).           */
 int mmf_plan_design(mmf_ctx* ctx, const double* X, int32_t n_rows, int32_t p,
                     int32_t t_fit, int32_t has_constant);
+/* CUDA-graph capture support.  A device-pointer call enqueued on a capturing stream records the library's kernels
+ * into the caller's graph; the graph then holds raw pointers to the context's scratch and to the planned design.
+ * mmf_pin_scratch(ctx, +1) after a capture makes every later call that would have to move that memory (a larger
+ * batch, mmf_plan_design) fail with MMF_E_UNSUPPORTED instead of leaving the graph with dangling pointers;
+ * mmf_pin_scratch(ctx, -1) when the graph is destroyed.  Counted: one +1 per live graph.
+ * replaces: nothing in the reference (Spark re-launches a Python task per group, 02:523-528); it is the B200
+ * answer to that per-task launch overhead for small batches.                                                   */
+int mmf_pin_scratch(mmf_ctx* ctx, int32_t delta);
 /* W [MMF_P*MMF_P] row-major (beta = W gamma), kept[MMF_P] 0/1; either may be NULL */
 int mmf_get_whitening(mmf_ctx* ctx, double* W, int32_t* kept);
 

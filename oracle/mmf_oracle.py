@@ -360,20 +360,27 @@ def select_forecast_packed(y: np.ndarray, X: np.ndarray, t_fit: int, n_hold: int
 # C restatement (oracle/mmf_oracle_c.c, pthreads): the fair multi-core CPU baseline
 # ----------------------------------------------------------------------------
 def fit_forecast_packed_c(y: np.ndarray, X: np.ndarray, t_fit: int, pred_start: int, n_pred: int, n_threads: int = 0,
-                          return_threads: bool = False):
+                          return_threads: bool = False, out=None, status=None, prepared=None):
     """Same contract as :func:`fit_forecast_packed`, computed by ``libmmf_oracle.so`` (float64 accumulation, one
-    pass per series, all host cores).  ``y`` float32 [N, ld]."""
+    pass per series, all host cores).  ``y`` float32 [N, ld].  ``out`` / ``status`` / ``prepared`` (the whitened
+    design from a previous call's ``prepared=`` dict) let a timed loop reuse its buffers instead of paying
+    page faults and the calendar whitening on every pass."""
     import ctypes as C
     import os
 
     lib = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmmf_oracle.so"))
     y = np.ascontiguousarray(y, dtype=np.float32)
-    W, kept = whiten(np.asarray(X, dtype=np.float64)[:t_fit])
-    A = np.ascontiguousarray(np.asarray(X, dtype=np.float64) @ W)
-    kept32 = np.ascontiguousarray(kept.astype(np.int32))
+    if prepared is not None and "A" in prepared:
+        A, kept32 = prepared["A"], prepared["kept32"]
+    else:
+        W, kept = whiten(np.asarray(X, dtype=np.float64)[:t_fit])
+        A = np.ascontiguousarray(np.asarray(X, dtype=np.float64) @ W)
+        kept32 = np.ascontiguousarray(kept.astype(np.int32))
+        if prepared is not None:
+            prepared["A"], prepared["kept32"] = A, kept32
     n = y.shape[0]
-    out = np.empty((n, n_pred), dtype=np.float64)
-    status = np.empty(n, dtype=np.int32)
+    out = np.empty((n, n_pred), dtype=np.float64) if out is None else out
+    status = np.empty(n, dtype=np.int32) if status is None else status
     lib.mmf_oracle_fit_forecast.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                             C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]
     lib.mmf_oracle_fit_forecast.restype = C.c_int
@@ -382,3 +389,27 @@ def fit_forecast_packed_c(y: np.ndarray, X: np.ndarray, t_fit: int, pred_start: 
     if return_threads:
         return out, status, int(used)
     return out, status
+
+
+def numa_local_sample(y: np.ndarray, n_threads: int = 0) -> np.ndarray:
+    """Copy of the float32 sample ``y`` [n, ld] whose pages were first touched by the pinned worker threads that
+    :func:`fit_forecast_packed_c` later assigns to the same rows (``mmf_oracle_alloc_local``): the timed CPU baseline
+    then reads socket-local memory on every box instead of wherever the calling thread happened to allocate."""
+    import ctypes as C
+    import os
+
+    lib = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmmf_oracle.so"))
+    lib.mmf_oracle_alloc_local.argtypes = [C.c_int64, C.c_int64, C.c_int32]
+    lib.mmf_oracle_alloc_local.restype = C.c_void_p
+    lib.mmf_oracle_free_local.argtypes = [C.c_void_p]
+    y = np.asarray(y, dtype=np.float32)
+    n, ld = y.shape
+    addr = lib.mmf_oracle_alloc_local(n, ld, n_threads)
+    if not addr:
+        raise MemoryError("mmf_oracle_alloc_local failed")
+    buf = (C.c_float * (n * ld)).from_address(addr)
+    arr = np.frombuffer(buf, dtype=np.float32).reshape(n, ld)
+    import weakref
+    weakref.finalize(buf, lib.mmf_oracle_free_local, addr)
+    arr[...] = y
+    return arr

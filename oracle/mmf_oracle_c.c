@@ -76,10 +76,35 @@ static int solve_masked(const float* y, const double* A, const int* kept, int t_
 typedef struct {
   const float* y; int64_t lo, hi, ld; int32_t t_fit; const double* A; const int* kp;
   int32_t pred_start, n_pred; double* out; int32_t* status;
+  int cpu;                    /* >= 0: pin the worker to this core (reproducible placement for the timed baseline) */
+  float* touch; size_t touch_bytes;   /* first-touch job: zero this slice from the pinned worker */
 } job_t;
+
+static void pin_self(int cpu) {
+  if (cpu < 0) return;
+  cpu_set_t one;
+  CPU_ZERO(&one);
+  CPU_SET(cpu, &one);
+  pthread_setaffinity_np(pthread_self(), sizeof(one), &one);
+}
+
+/* k-th core of the process affinity mask, or -1 */
+static int kth_cpu(const cpu_set_t* set, int k) {
+  for (int c = 0; c < CPU_SETSIZE; ++c)
+    if (CPU_ISSET(c, set) && k-- == 0) return c;
+  return -1;
+}
+
+static void* toucher(void* arg) {
+  const job_t* jb = (const job_t*)arg;
+  pin_self(jb->cpu);
+  memset(jb->touch, 0, jb->touch_bytes);
+  return NULL;
+}
 
 static void* worker(void* arg) {
   const job_t* jb = (const job_t*)arg;
+  pin_self(jb->cpu);
   const int32_t t_fit = jb->t_fit, n_pred = jb->n_pred;
   const double* A = jb->A;
   for (int64_t i = jb->lo; i < jb->hi; ++i) {
@@ -114,22 +139,50 @@ static void* worker(void* arg) {
   return NULL;
 }
 
-/* n_threads <= 0: one thread per core of the affinity mask.  Returns the number of threads used. */
+/* NUMA-aware sample buffer for the timed CPU baseline: n rows of ld floats whose pages are first touched by the same
+ * pinned thread (k-th core of the affinity mask, rows [k*per, (k+1)*per)) that mmf_oracle_fit_forecast later assigns to
+ * those rows, so every worker streams from its own socket's memory whatever box the bench lands on.  free() it with
+ * mmf_oracle_free_local.  The caller copies the sample in afterwards (the pages are already placed). */
+float* mmf_oracle_alloc_local(int64_t n, int64_t ld, int32_t n_threads) {
+  cpu_set_t set;
+  const int have = (sched_getaffinity(0, sizeof(set), &set) == 0) ? CPU_COUNT(&set) : 1;
+  if (n_threads <= 0) n_threads = have;
+  if ((int64_t)n_threads > n) n_threads = n > 0 ? (int)n : 1;
+  float* buf = NULL;
+  if (posix_memalign((void**)&buf, 4096, (size_t)n * (size_t)ld * sizeof(float) + 4096) != 0) return NULL;
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)n_threads);
+  job_t* jobs = (job_t*)calloc((size_t)n_threads, sizeof(job_t));
+  const int64_t per = (n + n_threads - 1) / n_threads;
+  for (int k = 0; k < n_threads; ++k) {
+    const int64_t lo = k * per < n ? k * per : n, hi = (lo + per < n) ? lo + per : n;
+    jobs[k].cpu = n_threads <= have ? kth_cpu(&set, k) : -1;
+    jobs[k].touch = buf + lo * ld;
+    jobs[k].touch_bytes = (size_t)(hi - lo) * (size_t)ld * sizeof(float);
+    pthread_create(&th[k], NULL, toucher, &jobs[k]);
+  }
+  for (int k = 0; k < n_threads; ++k) pthread_join(th[k], NULL);
+  free(th);
+  free(jobs);
+  return buf;
+}
+void mmf_oracle_free_local(float* p) { free(p); }
+
+/* n_threads <= 0: one thread per core of the affinity mask, each pinned to its core.  Returns the threads used. */
 int mmf_oracle_fit_forecast(const float* y, int64_t n, int64_t ld, int32_t t_fit, const double* A, const int32_t* kept,
                             int32_t pred_start, int32_t n_pred, double* out, int32_t* status, int32_t n_threads) {
   int kp[P];
   for (int j = 0; j < P; ++j) kp[j] = kept[j];
-  if (n_threads <= 0) {
-    cpu_set_t set;
-    n_threads = (sched_getaffinity(0, sizeof(set), &set) == 0) ? CPU_COUNT(&set) : 1;
-  }
+  cpu_set_t set;
+  const int have = (sched_getaffinity(0, sizeof(set), &set) == 0) ? CPU_COUNT(&set) : 1;
+  if (n_threads <= 0) n_threads = have;
   if ((int64_t)n_threads > n) n_threads = n > 0 ? (int)n : 1;
   pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)n_threads);
   job_t* jobs = (job_t*)malloc(sizeof(job_t) * (size_t)n_threads);
   const int64_t per = (n + n_threads - 1) / n_threads;
   for (int k = 0; k < n_threads; ++k) {
     const int64_t lo = k * per, hi = (lo + per < n) ? lo + per : n;
-    jobs[k] = (job_t){y, lo < n ? lo : n, hi, ld, t_fit, A, kp, pred_start, n_pred, out, status};
+    jobs[k] = (job_t){y, lo < n ? lo : n, hi, ld, t_fit, A, kp, pred_start, n_pred, out, status,
+                      n_threads <= have ? kth_cpu(&set, k) : -1, NULL, 0};
     pthread_create(&th[k], NULL, worker, &jobs[k]);
   }
   for (int k = 0; k < n_threads; ++k) pthread_join(th[k], NULL);

@@ -27,7 +27,24 @@ def oracle_golden():
 
 
 def tolerance(y):
-    """Stated fp32 tolerance of the CUDA path against the float64 oracle:
-    |yhat_gpu - yhat_ref| <= 1e-4 * max|y| + 1e-3 per element."""
+    """Stated fp32 tolerance of the CUDA path against the float64 oracle, well-conditioned rows:
+        |yhat_gpu - yhat_ref| <= 5e-6 * max|y| + 1e-3   per element.
+    fp32 epsilon at the data's scale is 6e-8 * max|y| per rounding; the 3-term tf32 split of the tensor-core path
+    (hi*A_hi + hi*A_lo + lo*A_hi) keeps the products at fp32 grade, and ~10^3 accumulated terms leave a few 1e-6
+    relative.  The bound is <= 4x the worst error measured on BASELINE config 2 (profiles/r02/parity_errors.md) and a
+    build with the lo*A_hi term compiled out FAILS it (tests/test_gpu_configs.py negative control).  Rows with an
+    ill-conditioned mask scale it by 1/min(1, min_pivot_ratio/0.25) (see test_parity_masked_series)."""
     import numpy as np
-    return 1e-4 * float(np.nanmax(np.abs(np.where(np.isfinite(y), y, 0.0)))) + 1e-3
+    return 5e-6 * float(np.nanmax(np.abs(np.where(np.isfinite(y), y, 0.0)))) + 1e-3
+
+
+def record_err(name, err, tol, **extra):
+    """Append one measured parity error to gpurun_out/parity_errors.jsonl (scratch; summarised under profiles/)."""
+    import json
+    d = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "parity_errors.jsonl"), "a") as f:
+            f.write(json.dumps({"test": name, "err": float(err), "tol": float(tol), **extra}) + "\n")
+    except OSError:
+        pass

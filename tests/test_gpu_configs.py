@@ -1,0 +1,293 @@
+"""GPU (-m gpu): BASELINE.json's configurations at their full sizes against the oracle, the negative control that
+proves the stated tolerance guards the tensor-core path's 3-term tf32 split, the fused multi-GPU path against the
+oracle (needs >= 2 GPUs, skipped otherwise), and the CUDA-graph / scratch lifetime rules of the C ABI.
+
+Every CUDA call goes ctypes -> libmmf.so (include/mmf.h); the oracle (oracle/, float64) is only the checker."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import mmf
+from conftest import ROOT, record_err, tolerance
+from oracle import mmf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _design(start, t, h, mode="future"):
+    if mode == "holdout":
+        grid = O.calendar_grid(start, t, "D")
+        return O.design_matrix(grid, t - h), t - h, 0, t
+    grid = O.calendar_grid(start, t + h, "D")
+    return O.design_matrix(grid, t), t, t, h
+
+
+def _le(err, tol, what=""):
+    name = os.environ.get("PYTEST_CURRENT_TEST", "?").split("::")[-1].split(" ")[0]
+    record_err(name, err, tol, what=str(what))
+    assert err <= tol, (what, float(err), float(tol))
+
+
+# ---- BASELINE configs[2]: 100k x 1,095, ALL rows against the oracle ------------------------------------
+@pytest.mark.parametrize("kernel", ["tc", "warp"])
+def test_parity_config3_100k_by_1095_all_rows(kernel):
+    """Every one of the 100,000 series against the float64 oracle (its C restatement, pinned to the NumPy oracle
+    by tests/test_oracle.py, runs them in a fraction of a second on the host cores)."""
+    import torch
+    n, t, h = 100_000, 1095, 28
+    yd, start = mmf.synth.daily_store_item_demand_torch(n, t, seed=4242)
+    y = yd.cpu().numpy()
+    want, wst = O.fit_forecast_packed_c(y, *_design(start, t, h))
+    eng = mmf.ForecastEngine(kernel=kernel)
+    res = mmf.forecast_packed(yd, start, "D", h, "future", engine=eng, want_status=True, want_stats=True)
+    torch.cuda.synchronize()
+    pred = res["pred"].cpu().numpy()
+    assert res["stats"].kernel_used == kernel
+    assert np.array_equal(res["status"].cpu().numpy(), wst) and (wst == 0).all()
+    _le(np.abs(pred - want).max(), tolerance(y), kernel)
+    eng.close()
+
+
+def test_parity_config3_holdout_and_gaps_all_rows():
+    """The reference contract (a value for every date, 02:484-494) and the gap path at configs[2] size, all rows."""
+    import torch
+    n, t, h = 100_000, 1095, 28
+    yd, start = mmf.synth.daily_store_item_demand_torch(n, t, seed=4243, nan_frac=0.01)
+    y = yd.cpu().numpy()
+    eng = mmf.ForecastEngine()
+    for mode in ("future", "holdout"):
+        X, t_fit, ps, npred = _design(start, t, h, mode)
+        want, wst = O.fit_forecast_packed_c(y, X, t_fit, ps, npred)
+        res = mmf.forecast_packed(yd, start, "D", h, mode, engine=eng, want_status=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(res["status"].cpu().numpy(), wst)
+        # ~11 gaps out of 1,095 rows: the per-series Gram stays well conditioned (pivot ratios ~ 0.99)
+        _le(np.abs(res["pred"].cpu().numpy() - want).max(), 2 * tolerance(y), mode)
+    eng.close()
+
+
+# ---- BASELINE configs[4]: 10M x 365 --------------------------------------------------------------------
+def test_config5_10m_by_365_device_and_host_spill():
+    """10 M series x 365 days (14.6 GB): (a) device-resident, (b) streamed from pinned host memory in chunks through
+    the 3-slot H2D / kernel / D2H pipeline (the "host-DRAM spill" of configs[4]).  (a) == (b) bit for bit on all
+    10 M rows, every status is OK, and an 8,192-row sample agrees with the oracle."""
+    import torch
+    n, t, h = 10_000_000, 365, 28
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40e9:
+        pytest.skip("needs 40 GB of free device memory")
+    yd, start = mmf.synth.daily_store_item_demand_torch(n, t, seed=55)       # [n, 365] view of a pitch-368 buffer
+    eng = mmf.ForecastEngine()
+    _, ps, npred = eng.plan_calendar(start, t, "D", h, "future")
+    dev = eng.fit_forecast(yd, ps, npred, want_status=True)
+    torch.cuda.synchronize()
+    assert int((dev["status"] != 0).sum()) == 0
+    idx = torch.randint(0, n, (8192,), device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    ys = yd[idx].cpu().numpy()
+    want, _ = O.fit_forecast_packed_c(ys, *_design(start, t, h))
+    _le(np.abs(dev["pred"][idx].cpu().numpy() - want).max(), tolerance(ys), "device-resident, 8192 sampled rows")
+    # host spill: the same rows from page-locked host memory, chunked
+    try:
+        yh = mmf.alloc_packed(n, t)                       # 14.7 GB pinned
+        oh = mmf.pinned_empty((n, h))
+    except mmf.MmfError:
+        pytest.skip("cannot pin 15 GB of host memory on this box")
+    torch.from_numpy(yh).copy_(yd)
+    eng2 = mmf.ForecastEngine(chunk_series=262_144)
+    eng2.plan_calendar(start, t, "D", h, "future")
+    res = eng2.fit_forecast(yh, ps, npred, out=oh, want_status=True, want_stats=True)
+    assert res["stats"].h2d_bytes == n * t * 4 and res["stats"].d2h_bytes >= n * h * 4
+    assert int((res["status"] != 0).sum()) == 0
+    got = torch.from_numpy(oh)
+    ref = dev["pred"].cpu()
+    assert torch.equal(got, ref), "host-spill path differs from the device-resident path"
+    record_err("test_config5_10m_by_365_device_and_host_spill", 0.0, 0.0, what="host spill == device bit for bit",
+               e2e_series_per_s=n / (res["stats"].total_ms * 1e-3))
+    eng.close()
+    eng2.close()
+    mmf.release_pinned_pool()
+
+
+# ---- negative control: the tolerance must catch a tf32-grade tensor-core path ------------------------------
+_NEGCTL = r"""
+import json, sys
+import numpy as np, torch
+sys.path.insert(0, {root!r})
+import mmf
+from oracle import mmf_oracle as O
+y, start = mmf.synth.daily_store_item_demand(10_000, 1095, seed=1234)
+grid = O.calendar_grid(start, 1095 + 28, "D")
+want, _ = O.fit_forecast_packed_c(y, O.design_matrix(grid, 1095), 1095, 1095, 28)
+eng = mmf.ForecastEngine(kernel="tc")
+pred = mmf.forecast_packed(mmf.device_packed(y), start, "D", 28, "future", engine=eng)
+torch.cuda.synchronize()
+err = np.abs(pred.cpu().numpy() - want)
+print(json.dumps({{"lib": mmf.LIB_PATH, "max_err": float(err.max()), "p99_row_err": float(np.percentile(err.max(axis=1), 99)),
+                  "rows_over": int((err.max(axis=1) > {tol}).sum()), "max_abs_y": float(np.abs(y).max())}}))
+"""
+
+
+def test_negative_control_without_lo_term_fails_config2():
+    """BASELINE configs[1] (10k x 1,095, all rows) through two builds of the same ABI: the product library must pass
+    the stated tolerance, and tests/_build/libmmf_negctl.so -- the tcgen05 kernel compiled WITHOUT the lo*A_hi MMA of
+    the 3-term tf32 split (-DMMF_TC_NO_LO_TERM) -- must FAIL it.  If the second half ever passes, the tolerance no
+    longer guards the property that makes the tensor-core path legitimate."""
+    neg = os.path.join(ROOT, "tests", "_build", "libmmf_negctl.so")
+    assert os.path.exists(neg), "negative-control library missing: run __graft_entry__.build()"
+    y, _ = mmf.synth.daily_store_item_demand(10_000, 1095, seed=1234)
+    tol = tolerance(y)
+    out = {}
+    for name, lib in (("product", ""), ("negctl", neg)):
+        env = dict(os.environ)
+        env.pop("MMF_LIB", None)
+        if lib:
+            env["MMF_LIB"] = lib
+        r = subprocess.run([sys.executable, "-c", _NEGCTL.format(root=ROOT, tol=tol)], env=env, capture_output=True,
+                           text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[name] = json.loads(r.stdout.strip().splitlines()[-1])
+        record_err("test_negative_control_without_lo_term_fails_config2", out[name]["max_err"], tol, what=name,
+                   **{k: v for k, v in out[name].items() if k != "max_err"})
+    assert out["negctl"]["lib"].endswith("libmmf_negctl.so") and out["product"]["lib"].endswith("libmmf.so")
+    assert out["product"]["max_err"] <= tol, out
+    assert out["negctl"]["max_err"] > tol, ("the tolerance does not detect a missing lo*A_hi term", out)
+    assert out["negctl"]["rows_over"] >= 100, out            # not one unlucky row: the whole batch degrades
+
+
+# ---- the fused multi-GPU path against the oracle -------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["p2p", "multicast-bulk"])
+def test_symmetric_table_fused_gather_matches_oracle(mode):
+    """world_size >= 2 (one process per GPU, torchrun): every rank fits its shard and the fit kernel's epilogue
+    stores each forecast tile into every rank's copy of the table (NVLink P2P bulk stores / NVLS multicast); every
+    rank's whole table must equal the ORACLE's forecasts of all shards (not just NCCL's gather of the same numbers),
+    including rows with gaps (fix-up kernels write through the same destinations)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = min(torch.cuda.device_count(), 8)
+    out = os.path.join(ROOT, "gpurun_out", f"symm_{mode}.json")
+    if os.path.exists(out):
+        os.remove(out)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29617", os.path.join(ROOT, "tests", "_symm_worker.py"),
+           "--mode", mode, "--out", out]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-4000:])
+    with open(out) as f:
+        res = json.load(f)
+    if res.get("skipped"):
+        pytest.skip(res["skipped"])
+    assert res["world"] == world
+    for rk in res["ranks"]:
+        _le(rk["max_err_vs_oracle"], res["tol"], f"rank {rk['rank']} {mode}")
+        assert rk["status_equal"] and rk["equals_nccl_gather"], rk
+
+
+# ---- CUDA-graph capture: counters and scratch lifetime ------------------------------------
+def test_capture_does_not_leave_stale_counters_for_eager_calls():
+    """The work counters are ping-ponged between eager calls and zeroed by the previous call's kernel; a capture only
+    RECORDS its kernels.  After capturing on gappy data (every row queues a record), eager calls and further
+    captures must still start from zero counters: no out-of-bounds record slots, no stale DEFERRED statuses."""
+    import torch
+    n, t, h = 4000, 400, 28
+    y, start = mmf.synth.daily_store_item_demand(n, t, seed=77, nan_frac=0.02)       # every row has gaps
+    want, wst = O.fit_forecast_packed(y, *_design(start, t, h))
+    eng = mmf.ForecastEngine()
+    _, ps, npred = eng.plan_calendar(start, t, "D", h, "future")
+    yd = mmf.device_packed(y)
+    graphs = []
+    for rep in range(3):                                  # several captures in a row, eager calls in between
+        st = torch.full((n,), -7, dtype=torch.int32, device="cuda")
+        g, out = eng.capture(yd, ps, npred, status=st)
+        graphs.append((g, out, st))
+        res = eng.fit_forecast(yd, ps, npred, want_status=True, want_stats=True)      # eager, no replay before it
+        torch.cuda.synchronize()
+        assert np.array_equal(res["status"].cpu().numpy(), wst), rep
+        assert res["stats"].n_pending < n
+        _le(np.abs(res["pred"].cpu().numpy() - want).max(), 2 * tolerance(y), f"eager after capture {rep}")
+    for g, out, st in graphs:                             # replays interleaved with eager calls
+        g.replay()
+        res = eng.fit_forecast(yd, ps, npred, want_status=True)
+        g.replay()
+        torch.cuda.synchronize()
+        assert np.array_equal(st.cpu().numpy(), wst) and np.array_equal(res["status"].cpu().numpy(), wst)
+        assert torch.equal(out, res["pred"])
+    for g, _, _ in graphs:
+        g.close()
+    eng.close()
+
+
+def test_captured_graph_pins_scratch_and_plan():
+    """A captured graph holds raw pointers into the context: re-planning or a larger batch must be refused while it
+    is alive (MMF_E_UNSUPPORTED), and work again once it is closed."""
+    import torch
+    n, t, h = 2000, 300, 28
+    y, start = mmf.synth.daily_store_item_demand(n, t, seed=3, nan_frac=0.01)
+    eng = mmf.ForecastEngine()
+    _, ps, npred = eng.plan_calendar(start, t, "D", h, "future")
+    yd = mmf.device_packed(y)
+    g, out = eng.capture(yd, ps, npred)
+    big = mmf.device_packed(np.tile(y, (3, 1)))
+    with pytest.raises(mmf.MmfError) as e1:
+        eng.fit_forecast(big, ps, npred)                  # needs 3x the record scratch
+    assert e1.value.code == -3 and "graph" in str(e1.value)
+    with pytest.raises(mmf.MmfError) as e2:
+        eng.plan_calendar(start, t, "D", 14, "future")    # another design would free the planned one
+    assert e2.value.code == -3
+    g.replay()                                            # still valid
+    torch.cuda.synchronize()
+    small = eng.fit_forecast(yd[:500], ps, npred)         # fits the existing scratch: allowed
+    torch.cuda.synchronize()
+    assert torch.equal(small, out[:500])
+    g.close()
+    eng.fit_forecast(big, ps, npred)                      # unpinned: scratch may grow again
+    eng.plan_calendar(start, t, "D", 14, "future")
+    torch.cuda.synchronize()
+    eng.close()
+
+
+def test_select_rejects_too_many_held_out_rows():
+    import torch
+    t, hold = 5000, 3600                                  # > MMF_SELECT_MAX_HOLD
+    y, start = mmf.synth.daily_store_item_demand(8, t, seed=1)
+    eng = mmf.ForecastEngine()
+    eng.plan_calendar(start, t, "D", hold, "holdout")
+    with pytest.raises(mmf.MmfError) as e:
+        eng.fit_select_forecast(mmf.device_packed(y), hold, (1, 16), 0, t)
+    assert e.value.code == -3 and "n_hold" in str(e.value)
+    eng.close()
+
+
+def test_mostly_missing_weekly_rows_take_the_direct_gram():
+    """Reference workload shape (weekly, 117 fit rows): rows with 59..88 missing weeks.  The in-stream gap path would
+    form G_i = I - sum a a^T with more than half the rows missing (catastrophic cancellation); they are routed to
+    the general pass, which builds the Gram over the observed rows -- so kernel=auto and kernel=warp agree."""
+    rng = np.random.default_rng(5)
+    df = mmf.synth.reference_weekly_demand(n_skus=2)
+    b = mmf.pack_groups(df, freq="W-MON", pinned=False)[0]
+    y0 = b.y[:1]
+    rows = []
+    for miss in (30, 58, 59, 60, 70, 80, 88):
+        r = y0[0].copy()
+        r[rng.choice(np.arange(1, 117), size=miss, replace=False)] = np.nan
+        rows.append(r)
+    y = np.stack(rows).astype(np.float32)
+    t, h = y.shape[1], 40
+    grid = O.calendar_grid(b.start, t, "W-MON")
+    want, wst, _, ratio = O.fit_forecast_packed(y, O.design_matrix(grid, t - h), t - h, 0, t, return_gamma=True)
+    outs = {}
+    for k in ("auto", "warp"):
+        eng = mmf.ForecastEngine(kernel=k)
+        res = mmf.forecast_packed(mmf.device_packed(y), b.start, "W-MON", h, "holdout", engine=eng, want_status=True)
+        outs[k] = res["pred"].cpu().numpy()
+        assert np.array_equal(res["status"].cpu().numpy(), wst), k
+        tol = tolerance(y) / np.minimum(1.0, ratio / 0.25)
+        rel = np.abs(outs[k] - want).max(axis=1) / tol
+        _le(rel.max(), 1.0, f"{k}: worst row error / row tolerance")
+        eng.close()
+    heavy = np.array([np.isnan(r[:t - h]).sum() * 2 > (t - h) for r in y])
+    assert heavy.any() and np.array_equal(outs["auto"][heavy], outs["warp"][heavy])      # same kernel, same bits
