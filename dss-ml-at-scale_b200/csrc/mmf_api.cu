@@ -111,6 +111,7 @@ struct mmf_ctx {
                                        // eager call's tcgen05 kernel); anything else makes the call memset its set
   int last_set = 0;                    // set the last enqueued call used (stats read n_pending from it)
   int pinned = 0;                      // > 0: a captured CUDA graph holds pointers into the scratch below and into the plan
+  bool status_scratch_captured = false;   // some capture ran without a caller-provided status buffer
   SolveRec* d_recs = nullptr;          // deferred masked series (grown on demand, capped)
   size_t recs_cap_bytes = 0;
   int64_t* d_rec_rows = nullptr;
@@ -265,6 +266,17 @@ int run_device(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, int32_t pr
     ctx->counter_set = cs ^ 1;
   }
   return MMF_OK;
+}
+
+// The status scratch is only referenced by a graph whose capture passed out_status == NULL; otherwise it may move.
+int grow_status_scratch(mmf_ctx* ctx, int64_t n, cudaStream_t s) {
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) ctx->status_scratch_captured = true;
+  const mmf_ctx* saved = g_grow_ctx;
+  if (!ctx->status_scratch_captured) g_grow_ctx = nullptr;
+  const int rc = grow((void**)&ctx->d_status_scratch, &ctx->status_scratch_cap, (size_t)n * sizeof(int32_t));
+  g_grow_ctx = saved;
+  return rc;
 }
 
 struct GrowScope {                                        // entry points that may reallocate scratch name their ctx
@@ -550,7 +562,7 @@ int mmf_fit_forecast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, 
     // ------------------------------------------------ all device: just enqueue
     int32_t* status = out_status;
     if (!status) {
-      int rc = grow((void**)&ctx->d_status_scratch, &ctx->status_scratch_cap, (size_t)n * sizeof(int32_t));
+      int rc = grow_status_scratch(ctx, n, ctx->stream);
       if (rc != MMF_OK) return rc;
       status = ctx->d_status_scratch;
     }
@@ -573,6 +585,8 @@ int mmf_fit_forecast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, 
     if (chunk > n) chunk = n;
     const int64_t pitch = (pl.t_fit + 3) & ~3;                 // staged row pitch (floats), TMA-friendly
     const int64_t opitch = (n_pred + 3) & ~3;
+    const mmf_ctx* pinned_scope = g_grow_ctx;
+    g_grow_ctx = nullptr;                                       // staging slots are never part of a captured graph
     for (int i = 0; i < NBUF; ++i) {
       Staging& s = ctx->st[i];
       int rc = MMF_OK;
@@ -580,8 +594,9 @@ int mmf_fit_forecast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, 
       if (rc == MMF_OK && !o_dev) rc = grow((void**)&s.d_out, &s.out_cap, (size_t)chunk * opitch * sizeof(float));
       if (rc == MMF_OK && out_beta && !b_dev) rc = grow((void**)&s.d_beta, &s.beta_cap, (size_t)chunk * P * sizeof(float));
       if (rc == MMF_OK && (!out_status || !s_dev)) rc = grow((void**)&s.d_status, &s.status_cap, (size_t)chunk * sizeof(int32_t));
-      if (rc != MMF_OK) return rc;
+      if (rc != MMF_OK) { g_grow_ctx = pinned_scope; return rc; }
     }
+    g_grow_ctx = pinned_scope;
     CU_TRY(cudaEventRecord(ctx->ev_a, ctx->stream));
     CU_TRY(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_a, 0));
     CU_TRY(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_a, 0));
@@ -676,7 +691,7 @@ int mmf_fit_forecast_bcast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t 
   if (!is_device_ptr(y)) return fail(MMF_E_INVALID, "the broadcast variant takes device buffers only");
   int32_t* status = out_status;
   if (!status) {
-    int rc = grow((void**)&ctx->d_status_scratch, &ctx->status_scratch_cap, (size_t)n * sizeof(int32_t));
+    int rc = grow_status_scratch(ctx, n, ctx->stream);
     if (rc != MMF_OK) return rc;
     status = ctx->d_status_scratch;
   }
@@ -713,7 +728,7 @@ int mmf_fit_select_forecast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t
   if (!is_device_ptr(y) || !is_device_ptr(out_pred)) return fail(MMF_E_INVALID, "device buffers only");
   int32_t* status = out_status;
   if (!status) {
-    int rc = grow((void**)&ctx->d_status_scratch, &ctx->status_scratch_cap, (size_t)n * sizeof(int32_t));
+    int rc = grow_status_scratch(ctx, n, ctx->stream);
     if (rc != MMF_OK) return rc;
     status = ctx->d_status_scratch;
   }

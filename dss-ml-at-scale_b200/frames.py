@@ -336,7 +336,8 @@ def _buckets_for(pdf, keys, date_col, value_col, freq, pack, eng):
 
 def forecast_groups(pdf, *, keys=DEFAULT_KEYS, date_col="Date", value_col="Demand",
                     freq="W-MON", horizon=FORECAST_HORIZON, mode="holdout", design="trend_season_exog",
-                    engine: ForecastEngine | None = None, pack: str = "host", select=None) -> pd.DataFrame:
+                    engine: ForecastEngine | None = None, pack: str = "host", select=None,
+                    null_keys_on_gaps: bool = False) -> pd.DataFrame:
     """Fit + forecast every group in ``pdf``; returns ``tuning_schema`` rows
     (keys..., Date, Demand, Demand_Fitted), groups in key order, dates ascending.
 
@@ -351,6 +352,11 @@ def forecast_groups(pdf, *, keys=DEFAULT_KEYS, date_col="Date", value_col="Deman
 
     ``pack="device"`` groups, sorts and re-grids the rows on the GPU (``packer.pack_table_device``: Arrow
     buffers in, padded series out) instead of with pandas on the host; ``pdf`` may then be an Arrow table.
+
+    ``null_keys_on_gaps=True`` (holdout mode) reproduces a detail of the reference's output assembly: it reads the
+    key columns from the re-indexed frame (02:490), so rows that ``asfreq`` inserted for missing dates carry NaN in
+    ``Product`` / ``SKU``.  By default the keys are filled on every row (a grid row without a ``Demand`` is still
+    that group's row); with the option, rows whose ``Demand`` is missing get null keys.
     """
     eng = engine or default_engine()
     keys = list(keys)
@@ -368,6 +374,11 @@ def forecast_groups(pdf, *, keys=DEFAULT_KEYS, date_col="Date", value_col="Deman
         else:
             frame[value_col] = np.full(n * n_pred, np.nan, dtype=np.float32)
         frame[fitted_col] = pred.reshape(-1)
+        if null_keys_on_gaps and mode == "holdout":
+            gap = np.isnan(frame[value_col])
+            if gap.any():
+                for k in keys:
+                    frame[k] = frame[k].astype(object).where(~gap, None)
         parts.append(pd.DataFrame(frame))
         lengths.append(n_pred)
     if not parts:
@@ -382,7 +393,8 @@ def forecast_groups(pdf, *, keys=DEFAULT_KEYS, date_col="Date", value_col="Deman
 
 def forecast_table(table, *, keys=DEFAULT_KEYS, date_col="Date", value_col="Demand",
                    freq="W-MON", horizon=FORECAST_HORIZON, mode="holdout", design="trend_season_exog",
-                   engine: ForecastEngine | None = None, pack: str = "host", select=None):
+                   engine: ForecastEngine | None = None, pack: str = "host", select=None,
+                   null_keys_on_gaps: bool = False):
     """Arrow ``Table``/``RecordBatch`` in -> Arrow ``Table`` with ``tuning_schema`` out (the ``mapInArrow``
     flavour of the boundary).  No pandas frame of the rows on either side: keys are dictionary-encoded on the way
     in and expanded from a dictionary on the way out, dates and values are NumPy views of Arrow buffers."""
@@ -399,13 +411,18 @@ def forecast_table(table, *, keys=DEFAULT_KEYS, date_col="Date", value_col="Dema
         n = y_host.shape[0]
         row_of = np.repeat(np.arange(n, dtype=np.int32), n_pred)
         cols = []
-        for k in keys:
-            kv = b.key_arrow[k] if b.key_arrow is not None else pa.array(b.key_frame[k].astype(str).to_numpy(dtype=object))
-            cols.append(_expand_strings(kv, row_of))
-        day32 = out_days.astype("datetime64[D]").astype(np.int32)
-        cols.append(pa.array(np.tile(day32, n)).cast(pa.date32()))
         demand = (np.ascontiguousarray(y_host).reshape(-1) if mode == "holdout"
                   else np.full(n * n_pred, np.nan, dtype=np.float32))
+        gap = np.isnan(demand) if (null_keys_on_gaps and mode == "holdout") else None
+        for k in keys:
+            kv = b.key_arrow[k] if b.key_arrow is not None else pa.array(b.key_frame[k].astype(str).to_numpy(dtype=object))
+            col = _expand_strings(kv, row_of)
+            if gap is not None and gap.any():                  # reference 02:490: asfreq rows have no key values
+                import pyarrow.compute as pc
+                col = pc.if_else(pa.array(gap), pa.scalar(None, pa.string()), col)
+            cols.append(col)
+        day32 = out_days.astype("datetime64[D]").astype(np.int32)
+        cols.append(pa.array(np.tile(day32, n)).cast(pa.date32()))
         cols.append(pa.array(demand, from_pandas=True))               # NaN -> null, like the pandas route
         cols.append(pa.array(np.ascontiguousarray(pred).reshape(-1), from_pandas=True))
         parts.append(pa.Table.from_arrays(cols, schema=schema))

@@ -264,9 +264,11 @@ def beta_from_gamma(gamma: np.ndarray, X_fit: np.ndarray) -> np.ndarray:
 # ----------------------------------------------------------------------------
 def build_tune_and_score_model(sku_pdf, *, keys=("Product", "SKU"), date_col="Date",
                                value_col="Demand", freq="W-MON", horizon=40,
-                               mode="holdout", design="trend_season_exog"):
+                               mode="holdout", design="trend_season_exog", null_keys_on_gaps=False):
     """One group's rows in -> one group's rows out (``tuning_schema``, 02:498-506):
-    keys..., Date, Demand, Demand_Fitted for every grid date."""
+    keys..., Date, Demand, Demand_Fitted for every grid date.  ``null_keys_on_gaps=True`` reproduces a detail of the
+    reference's output assembly (02:490): the key columns are read from the re-indexed frame, so the rows asfreq()
+    inserted for missing dates carry NaN keys."""
     import pandas as pd
 
     # 02:422-423  sort + regular grid (NaN for gaps)
@@ -277,12 +279,14 @@ def build_tune_and_score_model(sku_pdf, *, keys=("Product", "SKU"), date_col="Da
     T = (d1 - d0).days // step + 1
     grid = calendar_grid(d0, T, freq)
     y = np.full(T, np.nan)
+    present = np.zeros(T, dtype=bool)
     vals = pdf[value_col].to_numpy(dtype=np.float64)
     for d, v in zip(dates_in, vals):
         off = (d - d0).days
         if off % step:
             continue                                   # off-grid rows vanish under asfreq
         y[off // step] = v
+        present[off // step] = True
     key_vals = [pdf[k].iloc[0] for k in keys]          # 02:428-429
 
     if mode == "holdout":                              # 02:430, 372-380
@@ -302,6 +306,8 @@ def build_tune_and_score_model(sku_pdf, *, keys=("Product", "SKU"), date_col="Da
     out_dates = dates_all[pred_start:pred_start + n_pred]
     demand = y if mode == "holdout" else np.full(horizon, np.nan)
     out = {k: [v] * n_pred for k, v in zip(keys, key_vals)}
+    if null_keys_on_gaps and mode == "holdout":
+        out = {k: [v if p else None for v, p in zip(col, present)] for k, col in out.items()}
     out[date_col] = out_dates
     out[value_col] = demand.astype(np.float32)
     out[value_col + "_Fitted"] = pred[0].astype(np.float32)   # 02:490-494

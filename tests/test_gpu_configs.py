@@ -240,7 +240,8 @@ def test_captured_graph_pins_scratch_and_plan():
     assert e2.value.code == -3
     g.replay()                                            # still valid
     torch.cuda.synchronize()
-    small = eng.fit_forecast(yd[:500], ps, npred)         # fits the existing scratch: allowed
+    small = eng.fit_forecast(yd[:500], ps, npred)         # fits the existing scratch (the status scratch, which no
+                                                          # graph references, may still grow): allowed
     torch.cuda.synchronize()
     assert torch.equal(small, out[:500])
     g.close()
@@ -290,4 +291,6 @@ def test_mostly_missing_weekly_rows_take_the_direct_gram():
         _le(rel.max(), 1.0, f"{k}: worst row error / row tolerance")
         eng.close()
     heavy = np.array([np.isnan(r[:t - h]).sum() * 2 > (t - h) for r in y])
-    assert heavy.any() and np.array_equal(outs["auto"][heavy], outs["warp"][heavy])      # same kernel, same bits
+    assert heavy.any()
+    # same kernel and Gram route on both paths (row grouping inside a warp differs, so not the same bits)
+    _le(np.abs(outs["auto"][heavy] - outs["warp"][heavy]).max(), tolerance(y), "auto vs warp, mostly-missing rows")

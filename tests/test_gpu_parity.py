@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import mmf
-from conftest import record_err, tolerance
+from conftest import forecast_leverage, record_err, tolerance
 from oracle import mmf_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -86,7 +86,8 @@ def test_parity_full_series(engines, kernel, n, t):
     y, start = mmf.synth.daily_store_item_demand(n, t, seed=100 + n + t)
     want, wst = _oracle(y, start, "D", 28, "future")
     pred, status, _ = _run(engines[kernel], y, start, "D", 28, "future")
-    _le(np.abs(pred - want).max(), tolerance(y))
+    lev = forecast_leverage(O.design_matrix(O.calendar_grid(start, t + 28, "D"), t), t, t, 28)   # < 1 from t = 365 up
+    _le(np.abs(pred - want).max(), tolerance(y, lev), f"leverage {lev:.3g}")
     assert np.array_equal(status, wst)
 
 
