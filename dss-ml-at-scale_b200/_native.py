@@ -17,12 +17,15 @@ MMF_P = 16
 KERNEL_AUTO, KERNEL_WARP, KERNEL_TC = 0, 1, 2
 STATUS_OK, STATUS_EMPTY, STATUS_RANKDEF, STATUS_PENDING = 0, 1, 2, -1
 KERNELS = {"auto": KERNEL_AUTO, "warp": KERNEL_WARP, "tc": KERNEL_TC}
+DT_F32, DT_I16, DT_U16, DT_I32 = 0, 1, 2, 3
+INT_DTYPES = {"int16": DT_I16, "uint16": DT_U16, "int32": DT_I32}          # series element types besides float32
+INT_MISSING = {"int16": -32768, "uint16": 65535, "int32": -2147483648}     # the value that means "missing" in each
 
 # every symbol include/mmf.h declares (tests/test_abi.py checks the library exports them all)
 EXPORTS = (
     "mmf_version", "mmf_last_error", "mmf_device_count", "mmf_create", "mmf_destroy",
     "mmf_set_stream", "mmf_synchronize", "mmf_plan_design", "mmf_pin_scratch", "mmf_get_whitening",
-    "mmf_fit_forecast_f32", "mmf_fit_forecast_bcast_f32", "mmf_fit_select_forecast_f32", "mmf_pack_hash_utf8", "mmf_pack_hash_i32",
+    "mmf_fit_forecast_f32", "mmf_fit_forecast_int", "mmf_fit_forecast_bcast_f32", "mmf_fit_select_forecast_f32", "mmf_pack_hash_utf8", "mmf_pack_hash_i32",
     "mmf_pack_group_codes", "mmf_pack_verify_utf8", "mmf_pack_verify_i32", "mmf_pack_minmax", "mmf_pack_scatter_f32", "mmf_alloc_pinned", "mmf_free_pinned",
     "mmf_host_register", "mmf_host_unregister",
 )
@@ -86,6 +89,10 @@ def load() -> C.CDLL:
         C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
         C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(MmfStats),
     ]
+    lib.mmf_fit_forecast_int.argtypes = [
+        C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
+        C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(MmfStats),
+    ]
     lib.mmf_fit_forecast_bcast_f32.argtypes = [
         C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
         C.POINTER(C.c_uint64), C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
@@ -101,7 +108,7 @@ def load() -> C.CDLL:
     lib.mmf_pack_verify_i32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.mmf_pack_minmax.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
     lib.mmf_pack_scatter_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
-                                         C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int32]
+                                         C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]
     lib.mmf_alloc_pinned.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
     lib.mmf_free_pinned.argtypes = [C.c_void_p]
     lib.mmf_host_register.argtypes = [C.c_void_p, C.c_size_t]

@@ -88,6 +88,7 @@ constexpr int NBUF = 3;
 
 struct Staging {
   float* d_y = nullptr;      size_t y_cap = 0;        // bytes
+  void* d_yraw = nullptr;    size_t yraw_cap = 0;     // integer chunk as it left the host (mmf_fit_forecast_int)
   float* d_out = nullptr;    size_t out_cap = 0;
   float* d_beta = nullptr;   size_t beta_cap = 0;
   int32_t* d_status = nullptr; size_t status_cap = 0;
@@ -360,7 +361,7 @@ int mmf_destroy(mmf_ctx* ctx) {
   free_plan(ctx->plan);
   for (int i = 0; i < NBUF; ++i) {
     Staging& s = ctx->st[i];
-    cudaFree(s.d_y); cudaFree(s.d_out); cudaFree(s.d_beta); cudaFree(s.d_status);
+    cudaFree(s.d_y); cudaFree(s.d_yraw); cudaFree(s.d_out); cudaFree(s.d_beta); cudaFree(s.d_status);
     if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
     if (s.ev_comp) cudaEventDestroy(s.ev_comp);
     if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
@@ -535,9 +536,15 @@ int mmf_get_whitening(mmf_ctx* ctx, double* W, int32_t* kept) {
   return MMF_OK;
 }
 
-int mmf_fit_forecast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, int32_t pred_start, int32_t n_pred,
-                         float* out_pred, int64_t ld_out, float* out_beta, int32_t* out_status, mmf_stats* stats) {
+static int fit_forecast_impl(mmf_ctx* ctx, const void* y_any, int32_t dtype, int64_t n, int64_t ld_y, int32_t pred_start,
+                             int32_t n_pred, float* out_pred, int64_t ld_out, float* out_beta, int32_t* out_status,
+                             mmf_stats* stats) {
   if (!ctx) return fail(MMF_E_INVALID, "ctx is NULL");
+  if (dtype != MMF_DT_F32 && dtype != MMF_DT_I16 && dtype != MMF_DT_U16 && dtype != MMF_DT_I32)
+    return fail(MMF_E_INVALID, "dtype %d is not one of MMF_DT_F32 / I16 / U16 / I32", dtype);
+  const float* y = static_cast<const float*>(y_any);           // only dereferenced as float when dtype == MMF_DT_F32
+  const size_t esize = (dtype == MMF_DT_I16 || dtype == MMF_DT_U16) ? 2 : 4;
+  const bool is_int = dtype != MMF_DT_F32;
   GrowScope grow_scope(ctx);
   if (!ctx->plan.valid) return fail(MMF_E_NOPLAN, "mmf_plan_design has not been called");
   const Plan& pl = ctx->plan;
@@ -558,7 +565,7 @@ int mmf_fit_forecast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, 
   int launches = 0, kernel_used = 0;
   int64_t h2d = 0, d2h = 0;
 
-  if (y_dev && o_dev && b_dev && s_dev) {
+  if (!is_int && y_dev && o_dev && b_dev && s_dev) {
     // ------------------------------------------------ all device: just enqueue
     int32_t* status = out_status;
     if (!status) {
@@ -580,17 +587,19 @@ int mmf_fit_forecast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, 
       stats->n_pending = (kernel_used == MMF_KERNEL_TC) ? pend : 0;
     }
   } else {
-    // ------------------------------------------------ host buffers: pipelined chunks
+    // ------------------------------------------------ host buffers (or an integer series buffer): pipelined chunks
     int64_t chunk = ctx->cfg.chunk_series > 0 ? ctx->cfg.chunk_series : 32768;
     if (chunk > n) chunk = n;
     const int64_t pitch = (pl.t_fit + 3) & ~3;                 // staged row pitch (floats), TMA-friendly
+    const int64_t rpitch = (pl.t_fit + 7) & ~7;                // staged row pitch of an integer chunk (16-B rows)
     const int64_t opitch = (n_pred + 3) & ~3;
     const mmf_ctx* pinned_scope = g_grow_ctx;
     g_grow_ctx = nullptr;                                       // staging slots are never part of a captured graph
     for (int i = 0; i < NBUF; ++i) {
       Staging& s = ctx->st[i];
       int rc = MMF_OK;
-      if (!y_dev) rc = grow((void**)&s.d_y, &s.y_cap, (size_t)chunk * pitch * sizeof(float));
+      if (!y_dev || is_int) rc = grow((void**)&s.d_y, &s.y_cap, (size_t)chunk * pitch * sizeof(float));
+      if (rc == MMF_OK && is_int && !y_dev) rc = grow(&s.d_yraw, &s.yraw_cap, (size_t)chunk * rpitch * esize);
       if (rc == MMF_OK && !o_dev) rc = grow((void**)&s.d_out, &s.out_cap, (size_t)chunk * opitch * sizeof(float));
       if (rc == MMF_OK && out_beta && !b_dev) rc = grow((void**)&s.d_beta, &s.beta_cap, (size_t)chunk * P * sizeof(float));
       if (rc == MMF_OK && (!out_status || !s_dev)) rc = grow((void**)&s.d_status, &s.status_cap, (size_t)chunk * sizeof(int32_t));
@@ -605,7 +614,28 @@ int mmf_fit_forecast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, 
       const int64_t m = std::min(chunk, n - off);
       Staging& s = ctx->st[it % NBUF];
       const float* yk; int64_t ldk;
-      if (y_dev) { yk = y + off * ld_y; ldk = ld_y; }
+      if (is_int) {
+        // integer series: stage the chunk as it is (half / all of the float32 bytes), widen it on the device
+        const char* src = static_cast<const char*>(y_any) + (size_t)off * ld_y * esize;
+        if (it >= NBUF) CU_TRY(cudaStreamWaitEvent(y_dev ? ctx->stream : ctx->s_h2d, s.ev_comp, 0));   // d_y / d_yraw free again
+        const void* raw = src;
+        int64_t raw_ld = ld_y;
+        if (!y_dev) {
+          if (ld_y == rpitch)
+            CU_TRY(cudaMemcpyAsync(s.d_yraw, src, ((size_t)(m - 1) * rpitch + (size_t)pl.t_fit) * esize,
+                                   cudaMemcpyHostToDevice, ctx->s_h2d));
+          else
+            CU_TRY(cudaMemcpy2DAsync(s.d_yraw, (size_t)rpitch * esize, src, (size_t)ld_y * esize, (size_t)pl.t_fit * esize,
+                                     (size_t)m, cudaMemcpyHostToDevice, ctx->s_h2d));
+          CU_TRY(cudaEventRecord(s.ev_h2d, ctx->s_h2d));
+          CU_TRY(cudaStreamWaitEvent(ctx->stream, s.ev_h2d, 0));
+          raw = s.d_yraw; raw_ld = rpitch;
+          h2d += m * (int64_t)pl.t_fit * (int64_t)esize;
+        }
+        CU_TRY(launch_widen(dtype, raw, raw_ld, s.d_y, pitch, m, pl.t_fit, ctx->sm_count, ctx->stream));
+        ++launches;
+        yk = s.d_y; ldk = pitch;
+      } else if (y_dev) { yk = y + off * ld_y; ldk = ld_y; }
       else {
         if (it >= NBUF) CU_TRY(cudaStreamWaitEvent(ctx->s_h2d, s.ev_comp, 0));     // staging buffer free again
         if (ld_y == pitch)        // already pitched on the host: one contiguous copy (pad columns ride along, except
@@ -668,6 +698,18 @@ int mmf_fit_forecast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, 
     stats->kernel_used = kernel_used;
   }
   return MMF_OK;
+}
+
+int mmf_fit_forecast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, int32_t pred_start, int32_t n_pred,
+                         float* out_pred, int64_t ld_out, float* out_beta, int32_t* out_status, mmf_stats* stats) {
+  return fit_forecast_impl(ctx, y, MMF_DT_F32, n, ld_y, pred_start, n_pred, out_pred, ld_out, out_beta, out_status, stats);
+}
+
+int mmf_fit_forecast_int(mmf_ctx* ctx, const void* y, int32_t dtype, int64_t n, int64_t ld_y, int32_t pred_start,
+                         int32_t n_pred, float* out_pred, int64_t ld_out, float* out_beta, int32_t* out_status,
+                         mmf_stats* stats) {
+  if (dtype == MMF_DT_F32) return fail(MMF_E_INVALID, "mmf_fit_forecast_int takes MMF_DT_I16 / U16 / I32; use mmf_fit_forecast_f32");
+  return fit_forecast_impl(ctx, y, dtype, n, ld_y, pred_start, n_pred, out_pred, ld_out, out_beta, out_status, stats);
 }
 
 int mmf_fit_forecast_bcast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, int32_t pred_start,
@@ -800,11 +842,12 @@ int mmf_pack_minmax(mmf_ctx* ctx, const int32_t* gid, const int32_t* day, int64_
 
 int mmf_pack_scatter_f32(mmf_ctx* ctx, const int32_t* gid, const int32_t* day, const float* val, int64_t n,
                          const int64_t* row_of_group, const int32_t* gstart, int32_t step, float* y, int64_t n_rows,
-                         int64_t ld_y, int32_t t_len) {
+                         int64_t ld_y, int32_t t_len, uint64_t* duplicates) {
   PACK_PROLOGUE();
   if (step < 1 || ld_y % 4 != 0 || ld_y < t_len || (reinterpret_cast<uintptr_t>(y) & 15u) != 0)
     return fail(MMF_E_INVALID, "need step >= 1, a 16-B aligned y and ld_y >= t_len, ld_y %% 4 == 0");
-  CU_TRY(pack_scatter(gid, day, val, n, row_of_group, gstart, step, y, n_rows, ld_y, t_len, ctx->sm_count, ctx->stream));
+  CU_TRY(pack_scatter(gid, day, val, n, row_of_group, gstart, step, y, n_rows, ld_y, t_len,
+                      reinterpret_cast<unsigned long long*>(duplicates), ctx->sm_count, ctx->stream));
   return MMF_OK;
 }
 

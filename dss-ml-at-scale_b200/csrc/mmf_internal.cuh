@@ -111,6 +111,10 @@ struct SelectArgs {
 };
 cudaError_t launch_select(const DesignView& d, const FitArgs& a, const SelectArgs& sel, int sm_count, cudaStream_t s);
 
+// integer series -> float32 staging rows, sentinel -> NaN (widen.cu); dtype = MMF_DT_I16 / U16 / I32
+cudaError_t launch_widen(int dtype, const void* src, int64_t ld_src, float* dst, int64_t ld_dst, int64_t n, int32_t t,
+                         int sm_count, cudaStream_t s);
+
 // device-side packer (pack.cu)
 cudaError_t pack_hash_utf8(const int32_t* offsets, const uint8_t* data, int64_t n, uint64_t* h, int first, int sm,
                            cudaStream_t s);
@@ -126,7 +130,7 @@ cudaError_t pack_minmax(const int32_t* gid, const int32_t* day, int64_t n, int32
                         int32_t* gmax, int sm, cudaStream_t s);
 cudaError_t pack_scatter(const int32_t* gid, const int32_t* day, const float* val, int64_t n,
                          const int64_t* row_of_group, const int32_t* gstart, int32_t step, float* y, int64_t n_rows,
-                         int64_t ld_y, int32_t t_len, int sm, cudaStream_t s);
+                         int64_t ld_y, int32_t t_len, unsigned long long* dups, int sm, cudaStream_t s);
 
 #ifdef __CUDACC__
 // Forecast stores: plain, NVSwitch multicast (multimem.st) or fan-out over peer-mapped pointers.

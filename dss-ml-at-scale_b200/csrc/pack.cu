@@ -19,6 +19,7 @@ namespace mmf {
 namespace {
 
 constexpr int TPB = 256;
+constexpr unsigned PACK_FILL_BITS = 0x7fc00000u;   // the quiet NaN fill_nan_kernel writes: a cell no row has written yet
 
 __device__ __forceinline__ uint64_t fnv1a_byte(uint64_t h, uint32_t b) { return (h ^ b) * 1099511628211ull; }
 
@@ -119,7 +120,7 @@ __global__ void fill_nan_kernel(float4* __restrict__ y, int64_t n4) {
 __global__ void scatter_kernel(const int32_t* __restrict__ gid, const int32_t* __restrict__ day,
                                const float* __restrict__ val, int64_t n, const int64_t* __restrict__ row_of_group,
                                const int32_t* __restrict__ gstart, int32_t step, float* __restrict__ y, int64_t ld_y,
-                               int32_t t_len) {
+                               int32_t t_len, unsigned long long* __restrict__ dups) {
   for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += (int64_t)gridDim.x * TPB) {
     const int32_t g = gid[i];
     const int64_t r = row_of_group[g];
@@ -127,7 +128,13 @@ __global__ void scatter_kernel(const int32_t* __restrict__ gid, const int32_t* _
     const int32_t off = day[i] - gstart[g];
     if (off < 0 || off % step != 0) continue;       // off-grid rows vanish, like asfreq (02:423)
     const int32_t t = off / step;
-    if (t < t_len) y[r * ld_y + t] = val[i];
+    if (t >= t_len) continue;
+    if (dups == nullptr) { y[r * ld_y + t] = val[i]; continue; }
+    // duplicate (key, date) rows: the reference's asfreq raises on them (02:423).  Cells start as the fill NaN; an
+    // exchange that returns anything else means another row already landed here (a first row whose own value is that
+    // NaN is the one case this cannot see -- and there both rows mean "missing or overwritten" anyway).
+    const unsigned old = atomicExch(reinterpret_cast<unsigned*>(y + r * ld_y + t), __float_as_uint(val[i]));
+    if (old != PACK_FILL_BITS) atomicAdd(dups, 1ull);
   }
 }
 
@@ -240,10 +247,10 @@ cudaError_t pack_minmax(const int32_t* gid, const int32_t* day, int64_t n, int32
 
 cudaError_t pack_scatter(const int32_t* gid, const int32_t* day, const float* val, int64_t n,
                          const int64_t* row_of_group, const int32_t* gstart, int32_t step, float* y, int64_t n_rows,
-                         int64_t ld_y, int32_t t_len, int sm, cudaStream_t s) {
+                         int64_t ld_y, int32_t t_len, unsigned long long* dups, int sm, cudaStream_t s) {
   const int64_t n4 = n_rows * ld_y / 4;             // ld_y is a multiple of 4 floats and y is 16-B aligned
   if (n4 > 0) fill_nan_kernel<<<grid_for(n4, sm), TPB, 0, s>>>(reinterpret_cast<float4*>(y), n4);
-  if (n > 0) scatter_kernel<<<grid_for(n, sm), TPB, 0, s>>>(gid, day, val, n, row_of_group, gstart, step, y, ld_y, t_len);
+  if (n > 0) scatter_kernel<<<grid_for(n, sm), TPB, 0, s>>>(gid, day, val, n, row_of_group, gstart, step, y, ld_y, t_len, dups);
   return cudaGetLastError();
 }
 

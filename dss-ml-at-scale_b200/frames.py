@@ -219,10 +219,16 @@ def _pack_from_codes(gid, n_groups, days, vals, freq, pinned):
             row = local[gid]
             sel = (row >= 0) if on_grid is None else (on_grid & (row >= 0))
         idx = row * ld + pos
-        if sel is None:
-            flat[idx] = vals
+        if sel is not None:
+            idx, v = idx[sel], vals[sel]
         else:
-            flat[idx[sel]] = vals[sel]
+            v = vals
+        seen = np.zeros(flat.size, dtype=bool)
+        seen[idx] = True
+        if int(seen.sum()) != idx.size:        # the reference's set_index("Date").asfreq() raises here too (02:423)
+            raise ValueError(f"cannot reindex on an axis with duplicate labels: {idx.size - int(seen.sum())} rows repeat "
+                             f"a (group, date) combination")
+        flat[idx] = v
         out.append((int(start_day), int(tl), members, y))
     return out
 

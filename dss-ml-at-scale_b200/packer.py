@@ -43,6 +43,12 @@ def _stage_keys(table, keys, n, device):
     for k in keys:
         col = table.column(k)
         col = col.combine_chunks() if isinstance(col, pa.ChunkedArray) else col
+        if col.null_count and not pa.types.is_dictionary(col.type):
+            # the kernels read offsets / values, not the validity bitmap: give a null key its own dictionary code, so
+            # that it stays distinct from "" or 0 exactly like the host packer (null_encoding="encode")
+            col = pc.dictionary_encode(col, null_encoding="encode")
+        elif col.null_count:
+            col = pc.dictionary_encode(col.cast(col.type.value_type), null_encoding="encode")
         if pa.types.is_dictionary(col.type):
             idx = col.indices.cast(pa.int32()).to_numpy(zero_copy_only=False)
             staged.append(("i32", _dev_from_numpy(idx.astype(np.int32, copy=False), device)))
@@ -131,6 +137,8 @@ def pack_table_device(table, keys=("Product", "SKU"), date_col="Date", value_col
     step = D.FREQ_DAYS[freq]
 
     dcol = table.column(date_col).combine_chunks()
+    if dcol.null_count:
+        raise ValueError(f"{dcol.null_count} rows have a null {date_col}: a row without a date has no place on the grid")
     if not pa.types.is_date32(dcol.type):
         dcol = pc.cast(dcol, pa.date32())
     day = _dev_from_numpy(dcol.cast(pa.int32()).to_numpy(zero_copy_only=False), device)
@@ -155,6 +163,7 @@ def pack_table_device(table, keys=("Product", "SKU"), date_col="Date", value_col
     order = (key_frame.sort_values(keys, kind="stable").index.to_numpy() if sort_keys else np.arange(G))
 
     buckets = []
+    dups = torch.zeros(1, dtype=torch.int64, device=device)
     bucket_id, bucket_keys = pd.MultiIndex.from_arrays([gmin_h, t_len]).factorize(sort=True)
     for b, (start_day, tl) in enumerate(bucket_keys):
         members = order[bucket_id[order] == b]                        # group codes of this bucket, in key order
@@ -164,8 +173,13 @@ def pack_table_device(table, keys=("Product", "SKU"), date_col="Date", value_col
         ld = (int(tl) + 3) & ~3
         full = torch.empty((members.size, ld), dtype=torch.float32, device=device)
         N.check(lib.mmf_pack_scatter_f32(h, gid.data_ptr(), day.data_ptr(), val.data_ptr(), n, rog.data_ptr(),
-                                         gmin.data_ptr(), step, full.data_ptr(), members.size, ld, int(tl)))
+                                         gmin.data_ptr(), step, full.data_ptr(), members.size, ld, int(tl),
+                                         dups.data_ptr()))
         buckets.append(Bucket(np.datetime64(int(start_day), "D"), int(tl),
                               key_frame.iloc[members].reset_index(drop=True), full[:, :int(tl)]))
     torch.cuda.current_stream(device).synchronize()                   # the staged input tensors may be freed now
+    if int(dups.item()):
+        # the reference's set_index("Date").asfreq() raises on duplicate dates within a group (02:423)
+        raise ValueError(f"cannot reindex on an axis with duplicate labels: {int(dups.item())} rows repeat a "
+                         f"({', '.join(keys)}, {date_col}) combination")
     return buckets

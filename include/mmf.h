@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MMF_VERSION 100          /* 0.1.0 */
+#define MMF_VERSION 101          /* 0.1.1 */
 #define MMF_P 16                 /* design columns (zero-pad narrower designs) */
 #define MMF_PIVOT_TOL 1e-3f      /* per-series relative Cholesky pivot threshold */
 #define MMF_CAL_TOL 1e-10        /* aliasing threshold on the float64 calendar Gram */
@@ -50,6 +50,12 @@ extern "C" {
 #define MMF_STATUS_EMPTY 1       /* no observed fit row: outputs are NaN */
 #define MMF_STATUS_RANKDEF 2     /* ok, but a whitened column was dropped for this series' mask */
 #define MMF_STATUS_PENDING (-1)  /* internal: fast path saw a non-finite value, masked pass owes a result */
+
+/* element types of the series buffer (mmf_fit_forecast_int) and the value that means "missing" in each */
+#define MMF_DT_F32 0             /* float32, NaN / Inf = missing (mmf_fit_forecast_f32)  */
+#define MMF_DT_I16 1             /* int16,   -32768      = missing                        */
+#define MMF_DT_U16 2             /* uint16,  65535       = missing                        */
+#define MMF_DT_I32 3             /* int32,   INT32_MIN   = missing; exact for |v| < 2^24  */
 
 /* kernel selection */
 #define MMF_KERNEL_AUTO 0        /* tcgen05 fast path + masked fix-up where eligible, else warp kernel */
@@ -129,6 +135,17 @@ int mmf_fit_forecast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y,
                          float* out_pred, int64_t ld_out,
                          float* out_beta, int32_t* out_status, mmf_stats* stats);
 
+/* Same contract for an INTEGER series buffer y[n, ld_y] of element type `dtype` (MMF_DT_I16 / U16 / I32; ld_y in
+ * elements; host or device).  The reference's demand is integer valued (01-data-generator.py:304) and an int16 /
+ * uint16 value column halves the bytes that cross PCIe, which is what bounds the host-buffer path.  Chunks are
+ * staged as they are, widened to float32 on the device (sentinel -> missing) and fit by the same kernels: the
+ * results are bit-equal to mmf_fit_forecast_f32 on the float32 copy of the same values.
+ * replaces: the same lines as mmf_fit_forecast_f32, for a Demand column that arrives as ShortType / IntegerType. */
+int mmf_fit_forecast_int(mmf_ctx* ctx, const void* y, int32_t dtype, int64_t n, int64_t ld_y,
+                         int32_t pred_start, int32_t n_pred,
+                         float* out_pred, int64_t ld_out,
+                         float* out_beta, int32_t* out_status, mmf_stats* stats);
+
 /* ---- multi-GPU: fit + write the forecast rows into every GPU's copy of the table ----------
  * Same fit as above (device buffers only, enqueue-only), but each forecast row is stored to
  * n_out destinations in ONE kernel: out_ptrs[0] is this GPU's own slice, out_ptrs[1..] the same slice
@@ -166,7 +183,9 @@ int mmf_fit_select_forecast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t
  *                          the key of their group's first row, i.e. rows merged by a 64-bit hash collision
  *   minmax               : first / last day of every group
  *   scatter_f32          : y[row_of_group[g], (day - gstart[g]) / step] = value after a NaN fill; rows of groups with
- *                          row_of_group < 0 (other calendar buckets) and off-grid dates are skipped            */
+ *                          row_of_group < 0 (other calendar buckets) and off-grid dates are skipped.  `duplicates`
+ *                          (nullable device uint64, caller zeroes it) counts rows that landed on a (group, date)
+ *                          cell another row had already written: the reference's asfreq raises on those (02:423)  */
 int mmf_pack_hash_utf8(mmf_ctx* ctx, const int32_t* offsets, const uint8_t* data, int64_t n, uint64_t* hash,
                        int32_t first);
 int mmf_pack_hash_i32(mmf_ctx* ctx, const int32_t* values, int64_t n, uint64_t* hash, int32_t first);
@@ -180,7 +199,7 @@ int mmf_pack_minmax(mmf_ctx* ctx, const int32_t* gid, const int32_t* day, int64_
                     int32_t* gmin, int32_t* gmax);
 int mmf_pack_scatter_f32(mmf_ctx* ctx, const int32_t* gid, const int32_t* day, const float* val, int64_t n,
                          const int64_t* row_of_group, const int32_t* gstart, int32_t step, float* y, int64_t n_rows,
-                         int64_t ld_y, int32_t t_len);
+                         int64_t ld_y, int32_t t_len, uint64_t* duplicates);
 
 /* ---- host memory helpers (Arrow buffers -> one cudaMemcpyAsync) ---------- */
 int mmf_alloc_pinned(size_t bytes, void** out);

@@ -294,3 +294,37 @@ def test_mostly_missing_weekly_rows_take_the_direct_gram():
     assert heavy.any()
     # same kernel and Gram route on both paths (row grouping inside a warp differs, so not the same bits)
     _le(np.abs(outs["auto"][heavy] - outs["warp"][heavy]).max(), tolerance(y), "auto vs warp, mostly-missing rows")
+
+
+# ---- integer demand columns (int16 / uint16 / int32): half the PCIe bytes, bit-equal forecasts --------------------
+@pytest.mark.parametrize("dtype", ["uint16", "int16", "int32"])
+def test_integer_ingest_is_bit_equal_to_float32_ingest(dtype):
+    """mmf_fit_forecast_int: the reference's demand is integer valued (01-data-generator.py:304 round()); an integer
+    series buffer with the type's sentinel for missing values must produce exactly the float32 path's forecasts and
+    statuses -- host buffers (chunked, ragged last chunk, pitched and unpitched rows) and device buffers."""
+    import torch
+    n, t, h = 3001, 365, 28
+    y, start = mmf.synth.daily_store_item_demand(n, t, seed=31, nan_frac=0.003)
+    y = np.where(np.isfinite(y), np.clip(y, 0, 32000), np.nan).astype(np.float32)
+    y[17, :] = np.nan                                            # empty row
+    eng = mmf.ForecastEngine(chunk_series=700)
+    _, ps, npred = eng.plan_calendar(start, t, "D", h, "future")
+    want = eng.fit_forecast(mmf.device_packed(y), ps, npred, want_status=True)
+    torch.cuda.synchronize()
+    wp, ws = want["pred"].cpu().numpy(), want["status"].cpu().numpy()
+    yi = mmf.alloc_packed(n, t, dtype=dtype)                     # pinned, 16-B row pitch
+    mmf.to_integer_demand(y, dtype, out=yi)
+    res = eng.fit_forecast(yi, ps, npred, want_status=True, want_stats=True)
+    assert res["stats"].h2d_bytes == n * t * np.dtype(dtype).itemsize
+    assert np.array_equal(res["pred"], wp, equal_nan=True) and np.array_equal(res["status"], ws)
+    res2 = eng.fit_forecast(np.ascontiguousarray(yi), ps, npred)  # pageable, unpitched rows (ld = 365)
+    assert np.array_equal(res2, wp, equal_nan=True)
+    if dtype != "uint16":                                         # torch has no general uint16 support
+        yd = torch.from_numpy(np.ascontiguousarray(yi)).cuda()
+        res3 = eng.fit_forecast(yd, ps, npred, want_status=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(res3["pred"].cpu().numpy(), wp, equal_nan=True)
+        assert np.array_equal(res3["status"].cpu().numpy(), ws)
+    with pytest.raises(ValueError):
+        mmf.to_integer_demand(y + 0.5, dtype)
+    eng.close()

@@ -566,3 +566,34 @@ def test_epilogue_store_paths_for_various_horizons(engines, horizon):
         pred, status, _ = _run(engines[k], y, start, "D", horizon, "future")
         assert pred.shape == (517, horizon) and np.array_equal(status, wst)
         _le(np.abs(pred - want).max(), tolerance(y), (k, horizon))
+
+
+def test_device_packer_null_keys_null_dates_and_duplicates():
+    """ADVICE round 1: a null key is its own group (distinct from ""), like the host packer; a null date is rejected;
+    duplicate (key, date) rows raise like the reference's asfreq (02:423) instead of racing in the scatter."""
+    import pandas as pd
+    import pyarrow as pa
+    from mmf.packer import pack_table_device
+    rows = []
+    for sku in ("", None, "a"):
+        for i in range(12):
+            rows.append(("p", sku, dt.date(2021, 1, 4) + dt.timedelta(weeks=i), float(10 * i + (0 if sku is None else 1))))
+    df = pd.DataFrame(rows, columns=["Product", "SKU", "Date", "Demand"]).astype({"Demand": np.float32})
+    table = pa.Table.from_pandas(df, preserve_index=False)
+    assert table.column("SKU").null_count == 12
+    host = mmf.frames.pack_table_host(table, freq="W-MON", pinned=False)
+    dev = pack_table_device(table, freq="W-MON")
+    assert len(host) == len(dev) == 1 and dev[0].y.shape[0] == host[0].y.shape[0] == 3
+    hk = [None if pd.isna(v) else v for v in host[0].key_frame["SKU"].tolist()]
+    dk = [None if pd.isna(v) else v for v in dev[0].key_frame["SKU"].tolist()]
+    got = {k: dev[0].y[i].cpu().numpy() for i, k in enumerate(dk)}
+    want = {k: host[0].y[i] for i, k in enumerate(hk)}
+    assert set(got) == set(want) == {"", None, "a"}
+    for k in want:
+        assert np.array_equal(got[k], want[k], equal_nan=True), k
+    bad = pa.Table.from_pandas(df.assign(Date=[None] + df["Date"].tolist()[1:]), preserve_index=False)
+    with pytest.raises(ValueError, match="null"):
+        pack_table_device(bad, freq="W-MON")
+    dup = pa.Table.from_pandas(pd.concat([df, df.iloc[[5, 20]]], ignore_index=True), preserve_index=False)
+    with pytest.raises(ValueError, match="duplicate"):
+        pack_table_device(dup, freq="W-MON")

@@ -183,3 +183,14 @@ def test_sink_roundtrip(tmp_path):
     assert len(mmf.sink.read_forecasts(path)) == 3
     with pytest.raises(FileExistsError):
         mmf.sink.write_forecasts(df, path, mode="error")
+
+
+def test_duplicate_dates_raise_like_asfreq():
+    """The reference's set_index("Date").asfreq() raises on duplicate dates inside a group (02:423); so do the packers."""
+    import pyarrow as pa
+    df = _frame()
+    df = pd.concat([df, df.iloc[[3]]], ignore_index=True)
+    with pytest.raises(ValueError, match="duplicate"):
+        mmf.pack_groups(df, freq="W-MON", pinned=False)
+    with pytest.raises(ValueError, match="duplicate"):
+        mmf.frames.pack_table_host(pa.Table.from_pandas(df, preserve_index=False), freq="W-MON", pinned=False)
