@@ -43,6 +43,12 @@ def parse():
                          "(1 M groups over 8 GPUs + one all-gather of the forecast table)")
     ap.add_argument("--tc-variant", type=int, default=0, choices=[0, 1, 2],
                     help="tcgen05 kernel instantiation: 0 auto, 1 = 10 stages / 1 staging tile, 2 = 8 stages / 2 staging tiles")
+    ap.add_argument("--calendars", type=int, default=0,
+                    help="single GPU: ragged batch -- the series are split over this many distinct calendars (start dates "
+                         "one day apart, same length) and fit in ONE launch (mmf_fit_forecast_ragged_f32)")
+    ap.add_argument("--replicas", type=int, default=1,
+                    help="single GPU diagnostic: store every forecast tile to this many LOCAL copies of the table through the "
+                         "multi-destination epilogue (isolates its cost from NVLink)")
     ap.add_argument("--no-traffic", action="store_true", help="skip the live ncu DRAM-traffic probe of the dominant kernel")
     ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--t", type=int, default=1095)
@@ -386,10 +392,30 @@ def run_ours(args):
         graphs = [eng.capture(yy, ps, npred, out=mine)[0] for yy in ys]
     step_no = [0]
 
+    ragged_rows = None
+    if args.calendars > 0:
+        if world > 1 or args.mode != "future":
+            raise SystemExit("--calendars is a single-GPU, future-mode option")
+        C_ = args.calendars
+        ragged_rows = np.linspace(0, n, C_ + 1).astype(np.int64)
+        starts = [np.datetime64(start, "D") - np.timedelta64(c, "D") for c in range(C_)]
+        t0_plan = time.perf_counter()
+        eng.plan_calendars(starts, [t] * C_, "D", h)
+        ragged_plan_s = time.perf_counter() - t0_plan
+    reps = None
+    if args.replicas > 1 and world == 1:
+        rep_tensors = [torch.zeros_like(mine) for _ in range(args.replicas - 1)]     # kept alive by the closure below
+        reps = [mine.data_ptr()] + [r.data_ptr() for r in rep_tensors]
+
     def fit():
         i = step_no[0] % n_rot
         step_no[0] += 1
-        if graphs is not None:
+        if ragged_rows is not None:
+            eng.fit_forecast_ragged(ys[i], ragged_rows, out=mine)
+        elif reps is not None:
+            assert len(rep_tensors) == args.replicas - 1
+            eng.fit_forecast_bcast(ys[i], ps, npred, reps, h)
+        elif graphs is not None:
             graphs[i].replay()
         elif sym is not None:
             sym.fit_into(eng, ys[i], ps, npred)         # forecasts land in every rank's table from the epilogue
@@ -564,7 +590,10 @@ def run_ours(args):
                                         f"(BASELINE configs[3] shape; weak scaling)" if args.scaling == "weak" else
                                         f"{world * n} (store,item) series x {t} days in total, {n} per GPU (block-sharded), "
                                         f"{h}-day horizon, {args.mode} mode (BASELINE configs[3] as worded; strong scaling)"),
-                           "tc_variant": args.tc_variant,
+                           "tc_variant": args.tc_variant, "local_replicas": args.replicas,
+                           **({"calendars": args.calendars, "ragged_plan_seconds": ragged_plan_s,
+                               "ragged": "one launch over all calendars (mmf_fit_forecast_ragged_f32); every step "
+                                         "includes the call's one host synchronisation"} if args.calendars > 0 else {}),
                            "series_per_gpu": n, "t": t, "horizon": h, "nan_frac": args.nan_frac, "mode": args.mode,
                            "kernel": kernel_used,
                            "l2": (f"inputs {in_bytes / 1e9:.2f} GB per step per GPU > 126 MB L2" if n_rot == 1 else

@@ -93,11 +93,23 @@ __device__ __forceinline__ float centring_constant(const float* __restrict__ yro
   return c;
 }
 
-template <int STAGES, int OBUF>
+// MULTI: a ragged launch -- every 128-row tile names its calendar (mv.tiles / mv.cals); `n_chunks` is then only the
+// minimum over the calendars (>= 2).  MULTI == false compiles to the single-calendar kernel.
+template <int STAGES, int OBUF, bool MULTI>
 __global__ void __launch_bounds__(THREADS, 1)
 fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const FitArgs a,
-              uint32_t* __restrict__ pending_count, const int n_tiles, const int n_chunks) {
+              uint32_t* __restrict__ pending_count, const int n_tiles, const int n_chunks, const MultiView mv) {
   using SmemLayout = SmemLayoutT<STAGES, OBUF>;
+  auto tile_rec = [&](int ti) -> TileRec {
+    if (MULTI) {
+      if (ti >= n_tiles) return TileRec{0, 0, 0, 1};
+      const int4 v = __ldg(reinterpret_cast<const int4*>(mv.tiles) + ti);
+      return TileRec{v.x, v.y, v.z, v.w};
+    }
+    const int64_t left = a.n - (int64_t)ti * TILE_M;
+    return TileRec{ti * TILE_M, (int)(left >= TILE_M ? TILE_M : (left > 0 ? left : 0)), 0, n_chunks};
+  };
+  auto tfit_of = [&](const TileRec& t) -> int { return MULTI ? __ldg(&mv.cals[t.cal].t_fit) : d.t_fit; };
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   const uint32_t sbase = smem_u32(smem);
@@ -111,7 +123,7 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
 #ifdef MMF_TC_NO_COLLECT
   const bool collect = false;
 #else
-  const bool collect = a.recs != nullptr && d.t_fit <= 65535;
+  const bool collect = a.recs != nullptr && d.t_fit <= 65535;      // ragged: d.t_fit is the longest calendar's
 #endif
   const uint32_t s_bars = sbase + SmemLayout::bars;
   auto bar_full = [&](int s) { return s_bars + 8u * s; };
@@ -156,8 +168,9 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
       prefetch_tensormap(tl.tmap_at);
     }
   } else if (warp >= WARP_EPI0 && warp < WARP_PROD) {
-    // prediction rows of the whitened design -> shared (broadcast-read in the epilogue)
-    if (!a.skip_pred)
+    // prediction rows of the whitened design -> shared (broadcast-read in the epilogue); ragged launches reload
+    // them whenever the epilogue reaches a tile of another calendar
+    if (!a.skip_pred && !MULTI)
       for (int i = threadIdx.x - WARP_EPI0 * 32; i < a.n_pred * P; i += 128)
         s_apred[i] = __ldg(d.apred + (size_t)a.pred_start * P + i);
   }
@@ -171,12 +184,21 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
     // whole warp converged, one elected lane issues (keeps the tensor-map / barrier operands uniform)
     int stage = 0;
     uint32_t phase = 0;
+    int last_cal = -1;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      for (int ch = 0; ch < n_chunks; ++ch) {
+      const TileRec tr = tile_rec(tile);
+      // ragged: the y buffer seen through the calendar's own tensor map (clipped at ITS t_fit: later columns, which
+      // hold the held-out values or another calendar's padding, arrive as zeros) and the calendar's block of the
+      // stacked design
+      const void* tmy = MULTI ? static_cast<const void*>(mv.tmaps_y + (size_t)tr.cal * 128) : static_cast<const void*>(tl.tmap_y);
+      if (MULTI && tr.cal != last_cal) { fence_tensormap_acquire(tmy); last_cal = tr.cal; }
+      const int at_row = MULTI ? tr.cal * 2 * P : 0;
+      for (int ch = 0; ch < tr.n_chunks; ++ch) {
         mbar_wait(bar_empty(stage), phase ^ 1u);
         tma_load_2d_x2_elect(bar_full(stage), Y_STAGE_BYTES + AT_STAGE_BYTES,
-                             s_y + stage * Y_STAGE_BYTES, tl.tmap_y, ch * KC, tile * TILE_M, L2_EVICT_FIRST,
-                             s_at + stage * AT_STAGE_BYTES, tl.tmap_at, ch * KC, 0, L2_EVICT_LAST);
+                             s_y + stage * Y_STAGE_BYTES, tmy, ch * KC, tr.row0, L2_EVICT_FIRST,
+                             s_at + stage * AT_STAGE_BYTES, tl.tmap_at, ch * KC, at_row,
+                             MULTI ? L2_EVICT_NORMAL : L2_EVICT_LAST);   // one design stays in L2; a thousand do not
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
@@ -193,10 +215,11 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
     int lt = 0;                                      // local tile counter -> accumulator buffer lt & 1
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
       const int ab = lt & 1;
+      const int tile_chunks = MULTI ? tile_rec(tile).n_chunks : n_chunks;
       mbar_wait(bar_accempty(ab), ((lt >> 1) & 1) ^ 1u);    // epilogue of tile lt-2 has drained this buffer
       tc_fence_after();
       const uint32_t d_acc = tmem_base + ACC_COL0 + ab * 32;
-      for (int ch = 0; ch < n_chunks; ++ch) {
+      for (int ch = 0; ch < tile_chunks; ++ch) {
         const int aslot = grp ? aslot1 : aslot0;
         const uint32_t aphase = grp ? aphase1 : aphase0;
         mbar_wait(bar_full(stage), phase);                 // design chunk landed (same barrier as the y box)
@@ -215,7 +238,7 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
         }
         umma_commit_elect(bar_aempty(grp, aslot));
         umma_commit_elect(bar_empty(stage));
-        if (ch == n_chunks - 1) umma_commit_elect(bar_accfull(ab));
+        if (ch == tile_chunks - 1) umma_commit_elect(bar_accfull(ab));
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         if (grp) { if (++aslot1 == ASLOTS) { aslot1 = 0; aphase1 ^= 1u; } }
         else     { if (++aslot0 == ASLOTS) { aslot0 = 0; aphase0 ^= 1u; } }
@@ -235,15 +258,17 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
     int aslot = 0;
     uint32_t aphase = 0;
     int tile = blockIdx.x;
+    TileRec tr = tile_rec(tile);
     int ch = grp;
-    while (ch >= n_chunks && tile < n_tiles) { ch -= n_chunks; tile += gridDim.x; }   // n_chunks == 1 corner
-    auto load_c = [&](int tl_) -> float {
-      const int64_t row = (int64_t)tl_ * TILE_M + r;
-      return (d.has_constant && tl_ < n_tiles && row < a.n) ? centring_constant(a.y + row * a.ld_y, d.t_fit) : 0.f;
+    while (tile < n_tiles && ch >= tr.n_chunks) { ch -= tr.n_chunks; tile += gridDim.x; tr = tile_rec(tile); }   // 1-chunk corner
+    TileRec trn = tile_rec(tile + (int)gridDim.x);
+    auto load_c = [&](int tl_, const TileRec& t) -> float {
+      return (d.has_constant && tl_ < n_tiles && r < t.nrows)
+                 ? centring_constant(a.y + (int64_t)(t.row0 + r) * a.ld_y, tfit_of(t)) : 0.f;
     };
     auto finite = [](float x) { return (__float_as_uint(x) & 0x7f800000u) != 0x7f800000u; };
-    float c = load_c(tile);
-    float c_next = load_c(tile + (int)gridDim.x);       // one tile ahead: the latency hides under the tile
+    float c = load_c(tile, tr);
+    float c_next = load_c(tile + (int)gridDim.x, trn);  // one tile ahead: the latency hides under the tile
     bool bad = collect && !finite(c);                   // cannot centre on a missing first value: general path
     if (bad) c = 0.f;
     int nm = 0;                                         // missing values this thread saw in the current tile
@@ -255,7 +280,8 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
       float4 v[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) v[q] = lds128(rowp + ((static_cast<uint32_t>(q) ^ sw) << 4));
-      if (collect) {
+      // (ragged: rows of a partial tile beyond the calendar's last row belong to the NEXT tile -- never touch their records)
+      if (collect && (!MULTI || r < tr.nrows)) {
         float2 chk2 = make_float2(0.f, 0.f);            // 0 * x is NaN exactly when x is NaN or Inf
         const float2 zero2 = make_float2(0.f, 0.f);
 #pragma unroll
@@ -276,7 +302,7 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
           }
           // positions are shifted into a 64-bit register and leave four at a time (one 8-B store, the unit the
           // solve kernel reads): a 2-B store per gap made the record traffic the limiter of the gappy case
-          uint16_t* __restrict__ mt = a.recs[(int64_t)tile * TILE_M + r].miss_t + grp * SOLVE_SEG;
+          uint16_t* __restrict__ mt = a.recs[(int64_t)tr.row0 + r].miss_t + grp * SOLVE_SEG;
           const int tbase = ch * KC;
           while (gaps) {
             const int pos = __ffs(gaps) - 1;
@@ -306,10 +332,10 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
       const uint32_t a_hi = tmem_base + lane_addr + ASLOT_COL0 + (grp * ASLOTS + aslot) * 64;
       tmem_st_32x32b_x32(a_hi, hi);
       tmem_st_32x32b_x32(a_hi + 32, lo);
-      const bool last_own = collect && ch + NGROUPS >= n_chunks;       // my last chunk of this tile
+      const bool last_own = collect && ch + NGROUPS >= tr.n_chunks;    // my last chunk of this tile
       if (last_own) {
         if ((nm & 3) != 0 && nm < SOLVE_SEG) {          // flush the partial group (right-aligned: oldest first)
-          uint16_t* __restrict__ mt = a.recs[(int64_t)tile * TILE_M + r].miss_t + grp * SOLVE_SEG;
+          uint16_t* __restrict__ mt = a.recs[(int64_t)tr.row0 + r].miss_t + grp * SOLVE_SEG;
           *reinterpret_cast<unsigned long long*>(mt + (nm & ~3)) = packq >> (16 * (4 - (nm & 3)));
         }
         const int cnt = nm > 0x7ffe ? 0x7ffe : nm;
@@ -327,13 +353,15 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
       if (stage >= STAGES) { stage -= STAGES; phase ^= 1u; }
       if (++aslot == ASLOTS) { aslot = 0; aphase ^= 1u; }
       ch += NGROUPS;
-      while (ch >= n_chunks && tile < n_tiles) {        // next tile of this CTA
-        ch -= n_chunks;
+      while (tile < n_tiles && ch >= tr.n_chunks) {     // next tile of this CTA
+        ch -= tr.n_chunks;
         tile += gridDim.x;
         ++lt;
         nm = 0;
+        tr = trn;
+        trn = tile_rec(tile + (int)gridDim.x);
         c = c_next;
-        c_next = load_c(tile + (int)gridDim.x);
+        c_next = load_c(tile + (int)gridDim.x, trn);
         bad = collect && !finite(c);
         if (bad) c = 0.f;
       }
@@ -354,11 +382,28 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
 #endif
     const uint32_t s_ostage_u32 = smem_u32(s_ostage);
     int lt = 0;
+    int cur_cal = MULTI ? -1 : 0;
+    uint32_t kept_mask = d.kept_mask;
+    int t_fit_c = d.t_fit;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
       const int ab = lt & 1;
-      const int64_t row = (int64_t)tile * TILE_M + r;
-      const bool live = row < a.n;
-      float c = (d.has_constant && live) ? centring_constant(a.y + row * a.ld_y, d.t_fit) : 0.f;   // issued before the wait
+      const TileRec tr = tile_rec(tile);
+      const int64_t row = (int64_t)tr.row0 + r;
+      const bool live = r < tr.nrows;
+      if (MULTI && tr.cal != cur_cal) {                 // uniform over the four epilogue warps: they walk the same tiles
+        const int4* cp = reinterpret_cast<const int4*>(mv.cals + tr.cal);
+        const int4 m0 = __ldg(cp), m1 = __ldg(cp + 1);  // {t_fit, n_chunks, n_rows, kept_mask}, {row_off, pred_start, ..}
+        t_fit_c = m0.x;
+        kept_mask = static_cast<uint32_t>(m0.w);
+        if (!a.skip_pred) {
+          named_bar_sync(2, 128);                       // the previous tile's forecasts no longer read s_apred
+          const float* __restrict__ src = d.apred + (size_t)(m1.x + m1.y) * P;
+          for (int i = threadIdx.x - WARP_EPI0 * 32; i < a.n_pred * P; i += 128) s_apred[i] = __ldg(src + i);
+          named_bar_sync(2, 128);
+        }
+        cur_cal = tr.cal;
+      }
+      float c = (d.has_constant && live) ? centring_constant(a.y + row * a.ld_y, t_fit_c) : 0.f;   // issued before the wait
       mbar_wait(bar_accfull(ab), (lt >> 1) & 1);
       tc_fence_after();
       uint32_t acc[32];
@@ -369,13 +414,13 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
       if (collect) {
         mbar_wait(bar_nm(lt & (NM_RING - 1)), (lt / NM_RING) & 1);     // acquire the transform warps' counts
         const uint16_t* nmrow = s_nm + (lt & (NM_RING - 1)) * NGROUPS * TILE_M + r;
-        const bool has0 = n_chunks >= 2 || ((lt * n_chunks) & 1) == 0;
+        const bool has0 = n_chunks >= 2 || ((lt * n_chunks) & 1) == 0;      // (ragged launches: every calendar has >= 2 chunks)
         const bool has1 = n_chunks >= 2 || ((lt * n_chunks) & 1) == 1;
         const unsigned f0 = has0 ? nmrow[0] : 0u, f1 = has1 ? nmrow[TILE_M] : 0u;
         nm0 = f0 & 0x7fff; nm1 = f1 & 0x7fff;
         // mostly-missing rows: the downdate I - sum a a^T cancels catastrophically; fit_warp builds their Gram
         // directly over the observed rows (same rule as fit_warp.cu)
-        general = ((f0 | f1) & 0x8000u) != 0u || nm0 > SOLVE_SEG || nm1 > SOLVE_SEG || 2 * (nm0 + nm1) > d.t_fit;
+        general = ((f0 | f1) & 0x8000u) != 0u || nm0 > SOLVE_SEG || nm1 > SOLVE_SEG || 2 * (nm0 + nm1) > t_fit_c;
         if (general) c = 0.f;
       }
       tmem_wait_ld();
@@ -388,12 +433,15 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
       for (int p = 0; p < P; ++p) {
         g[p] = __uint_as_float(acc[p]) + __uint_as_float(acc[P + p]);
         finite = finite && ((__float_as_uint(g[p]) & 0x7f800000u) != 0x7f800000u);
-        if (!((d.kept_mask >> p) & 1u)) g[p] = 0.f;
+        if (!((kept_mask >> p) & 1u)) g[p] = 0.f;
       }
       const bool pend = live && (!finite || general);            // -> general warp pass
       const bool defer = live && !pend && (nm0 + nm1) > 0;       // -> thread-per-series solve of the queued record
       const unsigned pm = __ballot_sync(0xffffffffu, pend);
-      if (lane == 0 && pm != 0u) atomicAdd(pending_count, __popc(pm));
+      if (lane == 0 && pm != 0u) {
+        atomicAdd(pending_count, __popc(pm));
+        if (MULTI) atomicAdd(mv.pending_by_cal + tr.cal, __popc(pm));      // the general pass runs per calendar
+      }
       const unsigned dm = __ballot_sync(0xffffffffu, defer);
       if (dm != 0u) {
         unsigned base = 0;
@@ -407,6 +455,7 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
           rec.c = c;
           rec.nm[0] = static_cast<uint16_t>(nm0);
           rec.nm[1] = static_cast<uint16_t>(nm1);
+          rec.cal = tr.cal;
           const unsigned slot = base + __popc(dm & ((1u << lane) - 1u));
           if (slot < a.rec_cap) a.rec_rows[slot] = row;
         }
@@ -426,9 +475,8 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
         if (warp == WARP_EPI0) {
-          const int64_t rows_here = (a.n - (int64_t)tile * TILE_M) < TILE_M ? (a.n - (int64_t)tile * TILE_M) : TILE_M;
-          const uint32_t bytes = static_cast<uint32_t>(rows_here) * a.n_pred * 4u;
-          const int64_t off = (int64_t)tile * TILE_M * a.n_pred;
+          const uint32_t bytes = static_cast<uint32_t>(tr.nrows) * a.n_pred * 4u;
+          const int64_t off = (int64_t)tr.row0 * a.n_pred;
           const uint32_t src = s_ostage_u32 + static_cast<uint32_t>(ob) * (TILE_M * BULK_MAX_PRED * 4);
           bulk_store_elect(reinterpret_cast<uint64_t>(a.out + off), src, bytes);
           // peers: every tile starts at another peer, so at any moment this GPU's 148 store queues target all
@@ -503,26 +551,29 @@ bool fit_tc_supported(const DesignView& d, const FitArgs& a, const char** why) {
   return w == nullptr;
 }
 
-template <int STAGES, int OBUF>
+template <int STAGES, int OBUF, bool MULTI>
 static cudaError_t launch_variant(const DesignView& d, const FitArgs& a, const TcLaunch& tl, uint32_t* pending_count,
-                                  int sm_count, cudaStream_t s, int n_tiles, int n_chunks) {
+                                  int sm_count, cudaStream_t s, int n_tiles, int n_chunks, const MultiView& mv) {
   const size_t smem = SmemLayoutT<STAGES, OBUF>::total + 1024;
-  cudaError_t e = cudaFuncSetAttribute(fit_tc_kernel<STAGES, OBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(fit_tc_kernel<STAGES, OBUF, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int grid = n_tiles < sm_count ? n_tiles : sm_count;
-  fit_tc_kernel<STAGES, OBUF><<<grid, THREADS, smem, s>>>(tl, d, a, pending_count, n_tiles, n_chunks);
+  fit_tc_kernel<STAGES, OBUF, MULTI><<<grid, THREADS, smem, s>>>(tl, d, a, pending_count, n_tiles, n_chunks, mv);
   return cudaGetLastError();
 }
 
 cudaError_t launch_fit_tc(const DesignView& d, const FitArgs& a, const TcLaunch& tl, uint32_t* pending_count,
-                          int sm_count, cudaStream_t s, int variant) {
+                          int sm_count, cudaStream_t s, int variant, const MultiView* multi) {
   if (a.n <= 0) return cudaSuccess;
+  if (multi != nullptr)      // ragged: the tile table names rows and calendars; d.t_pad / KC is the LONGEST calendar's count
+    return launch_variant<10, 1, true>(d, a, tl, pending_count, sm_count, s, multi->n_tiles, 2, *multi);
   const int n_tiles = (int)((a.n + TILE_M - 1) / TILE_M);
   const int n_chunks = d.t_pad / KC;
+  const MultiView none{};
   // variant 0 = automatic: two staging tiles as soon as a tile has more than one destination
   const bool two = variant == 2 || (variant == 0 && (a.n_out > 1 || a.out_multimem == 2));
-  return two ? launch_variant<8, 2>(d, a, tl, pending_count, sm_count, s, n_tiles, n_chunks)
-             : launch_variant<10, 1>(d, a, tl, pending_count, sm_count, s, n_tiles, n_chunks);
+  return two ? launch_variant<8, 2, false>(d, a, tl, pending_count, sm_count, s, n_tiles, n_chunks, none)
+             : launch_variant<10, 1, false>(d, a, tl, pending_count, sm_count, s, n_tiles, n_chunks, none);
 }
 
 }  // namespace mmf

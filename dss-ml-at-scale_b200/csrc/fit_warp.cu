@@ -363,8 +363,9 @@ fit_warp_kernel(const DesignView d, const FitArgs a, const int smem_rows) {
           rec.c = cs;
           rec.nm[0] = (uint16_t)(nm < SOLVE_SEG ? nm : SOLVE_SEG);
           rec.nm[1] = (uint16_t)(nm < SOLVE_SEG ? 0 : nm - SOLVE_SEG);
+          rec.cal = a.cal_id;
           const unsigned slot = atomicAdd(a.rec_count, 1u);
-          if (slot < a.rec_cap) a.rec_rows[slot] = row0 + s;
+          if (slot < a.rec_cap) a.rec_rows[slot] = a.row_base + row0 + s;
         }
         for (int m = lane; m < nm; m += 32) rec.miss_t[m] = scr.miss_t[s][m];   // segment 1 starts at SOLVE_SEG
         if (lane < ((nm + 3) & ~3) - nm) rec.miss_t[nm + lane] = 0;             // the solve kernel reads whole 8-B groups

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -84,6 +85,25 @@ struct Plan {
   alignas(64) unsigned char tmap_blo[128];
 };
 
+// Ragged plan: the whitened designs of many calendars stacked
+struct MultiPlan {
+  bool valid = false;
+  int32_t n_cal = 0, n_pred = 0, has_constant = 0, t_fit_max = 0, t_pad_max = 0, min_chunks = 0;
+  std::vector<CalMeta> cals;           // host copy of d_cals
+  std::vector<size_t> a4_off;          // float4 offset of every calendar's a4 block
+  CalMeta* d_cals = nullptr;
+  float* d_at = nullptr;               // [n_cal * 32][t_pad_max]: hi / lo of A^T per calendar (TMA B operand)
+  float* d_apred = nullptr;            // [sum n_rows][P]
+  float4* d_a4 = nullptr;              // per-calendar column-blocked blocks (general pass)
+  float* d_w = nullptr;                // zeros (beta is not offered for ragged batches)
+  uint32_t* d_pending_by_cal = nullptr;
+  alignas(64) unsigned char tmap_at[128];
+  // per-call tables, kept while the same buffer / row layout is fit again
+  TileRec* d_tiles = nullptr;  size_t tiles_cap = 0;  int32_t n_tiles = 0;
+  unsigned char* d_tmaps_y = nullptr;
+  const void* key_y = nullptr;  int64_t key_n = -1, key_ld = -1;  std::vector<int64_t> key_rows;
+};
+
 constexpr int NBUF = 3;
 
 struct Staging {
@@ -126,10 +146,17 @@ struct mmf_ctx {
   void* d_pack_scratch = nullptr;      // sort / scan work space of the packer (grown on demand, kept)
   size_t pack_scratch_cap = 0;
   Plan plan;
+  MultiPlan multi;
   Staging st[NBUF];
 };
 
 namespace {
+
+void free_multi(MultiPlan& m) {
+  cudaFree(m.d_cals); cudaFree(m.d_at); cudaFree(m.d_apred); cudaFree(m.d_a4); cudaFree(m.d_w);
+  cudaFree(m.d_pending_by_cal); cudaFree(m.d_tiles); cudaFree(m.d_tmaps_y);
+  m = MultiPlan{};
+}
 
 void free_plan(Plan& p) {
   cudaFree(p.d_a4); cudaFree(p.d_at); cudaFree(p.d_apred); cudaFree(p.d_w); cudaFree(p.d_ap_hi); cudaFree(p.d_ap_lo);
@@ -164,6 +191,65 @@ DesignView view_of(const Plan& p) {
   d.n_rows = p.n_rows; d.n_rows_pad = p.n_rows_pad; d.t_fit = p.t_fit; d.t_pad = p.t_pad;
   d.kept_mask = p.kept_mask; d.has_constant = p.has_constant;
   return d;
+}
+
+
+// float64 calendar Gram over the fit rows, in-order Cholesky with aliasing, W = L^-T on the kept columns
+// (oracle/mmf_oracle.py: whiten), A = X W in float32.  Shared by the single-calendar and the ragged plan.
+void whiten_calendar(const double* X, int32_t n_rows, int32_t p, int32_t t_fit, double* W /*[P*P]*/, uint32_t* kept_mask,
+                     std::vector<float>& A /*[n_rows*P]*/) {
+  double G[P][P] = {}, L[P][P] = {};
+  for (int32_t t = 0; t < t_fit; ++t) {
+    const double* x = X + (int64_t)t * p;
+    for (int i = 0; i < p; ++i)
+      for (int j = 0; j <= i; ++j) G[i][j] += x[i] * x[j];
+  }
+  for (int i = 0; i < P; ++i)
+    for (int j = 0; j < i; ++j) G[j][i] = G[i][j];
+  bool kept[P] = {};
+  for (int j = 0; j < P; ++j) {
+    double dsum = G[j][j];
+    for (int k = 0; k < j; ++k) dsum -= L[j][k] * L[j][k];
+    if (G[j][j] <= 0.0 || dsum <= MMF_CAL_TOL * G[j][j]) continue;
+    kept[j] = true;
+    L[j][j] = std::sqrt(dsum);
+    for (int i = j + 1; i < P; ++i) {
+      double sacc = G[i][j];
+      for (int k = 0; k < j; ++k) sacc -= L[i][k] * L[j][k];
+      L[i][j] = sacc / L[j][j];
+    }
+  }
+  int idx[P], nk = 0;
+  for (int j = 0; j < P; ++j) if (kept[j]) idx[nk++] = j;
+  double M[P][P] = {};
+  for (int c = 0; c < nk; ++c) {
+    for (int r = 0; r < nk; ++r) {
+      double sacc = (r == c) ? 1.0 : 0.0;
+      for (int k = 0; k < r; ++k) sacc -= L[idx[r]][idx[k]] * M[k][c];
+      M[r][c] = sacc / L[idx[r]][idx[r]];
+    }
+  }
+  for (int i = 0; i < P * P; ++i) W[i] = 0.0;
+  for (int a = 0; a < nk; ++a)
+    for (int b = 0; b < nk; ++b) W[idx[a] * P + idx[b]] = M[b][a];
+  *kept_mask = 0;
+  for (int j = 0; j < P; ++j) if (kept[j]) *kept_mask |= 1u << j;
+  A.assign((size_t)n_rows * P, 0.f);
+  for (int32_t t = 0; t < n_rows; ++t) {
+    const double* x = X + (int64_t)t * p;
+    for (int q = 0; q < P; ++q) {
+      double sacc = 0.0;
+      for (int i = 0; i < p; ++i) sacc += x[i] * W[i * P + q];
+      A[(size_t)t * P + q] = (float)sacc;
+    }
+  }
+}
+
+inline void split_tf32(float v, float* hi, float* lo) {
+  uint32_t hb; memcpy(&hb, &v, 4); hb &= 0xFFFFE000u;
+  memcpy(hi, &hb, 4);
+  float l = v - *hi;
+  uint32_t lb; memcpy(&lb, &l, 4); lb &= 0xFFFFE000u; memcpy(lo, &lb, 4);
 }
 
 // Enqueue the fit for device-resident buffers on `s`.  status must be non-null.
@@ -359,6 +445,7 @@ int mmf_destroy(mmf_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   free_plan(ctx->plan);
+  free_multi(ctx->multi);
   for (int i = 0; i < NBUF; ++i) {
     Staging& s = ctx->st[i];
     cudaFree(s.d_y); cudaFree(s.d_yraw); cudaFree(s.d_out); cudaFree(s.d_beta); cudaFree(s.d_status);
@@ -418,61 +505,14 @@ int mmf_plan_design(mmf_ctx* ctx, const double* X, int32_t n_rows, int32_t p, in
   free_plan(ctx->plan);
   Plan& pl = ctx->plan;
 
-  // ---- float64 calendar Gram, in-order Cholesky with aliasing (oracle/mmf_oracle.py: whiten)
-  double G[P][P] = {}, L[P][P] = {};
-  for (int32_t t = 0; t < t_fit; ++t) {
-    const double* x = X + (int64_t)t * p;
-    for (int i = 0; i < p; ++i)
-      for (int j = 0; j <= i; ++j) G[i][j] += x[i] * x[j];
-  }
-  for (int i = 0; i < P; ++i)
-    for (int j = 0; j < i; ++j) G[j][i] = G[i][j];
-  bool kept[P] = {};
-  for (int j = 0; j < P; ++j) {
-    double dsum = G[j][j];
-    for (int k = 0; k < j; ++k) dsum -= L[j][k] * L[j][k];
-    if (G[j][j] <= 0.0 || dsum <= MMF_CAL_TOL * G[j][j]) continue;
-    kept[j] = true;
-    L[j][j] = std::sqrt(dsum);
-    for (int i = j + 1; i < P; ++i) {
-      double s = G[i][j];
-      for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
-      L[i][j] = s / L[j][j];
-    }
-  }
-  // W = L^-T restricted to the kept set.  Solve L M = I column by column (M = L^-1), W = M^T.
-  int idx[P], nk = 0;
-  for (int j = 0; j < P; ++j) if (kept[j]) idx[nk++] = j;
-  double M[P][P] = {};
-  for (int c = 0; c < nk; ++c) {
-    for (int r = 0; r < nk; ++r) {
-      double s = (r == c) ? 1.0 : 0.0;
-      for (int k = 0; k < r; ++k) s -= L[idx[r]][idx[k]] * M[k][c];
-      M[r][c] = s / L[idx[r]][idx[r]];
-    }
-  }
-  for (int i = 0; i < P * P; ++i) pl.W[i] = 0.0;
-  for (int a = 0; a < nk; ++a)
-    for (int b = 0; b < nk; ++b) pl.W[idx[a] * P + idx[b]] = M[b][a];
-  pl.kept_mask = 0;
-  for (int j = 0; j < P; ++j) if (kept[j]) pl.kept_mask |= 1u << j;
-
+  // ---- float64 calendar Gram, in-order Cholesky with aliasing, A = X W (whiten_calendar above)
   pl.n_rows = n_rows;
   pl.n_rows_pad = (n_rows + 31) & ~31;
   pl.t_fit = t_fit;
   pl.t_pad = (t_fit + 31) & ~31;
   pl.has_constant = has_constant ? 1 : 0;
-
-  // ---- A = X W in the three device layouts
-  std::vector<float> A((size_t)n_rows * P, 0.f);
-  for (int32_t t = 0; t < n_rows; ++t) {
-    const double* x = X + (int64_t)t * p;
-    for (int q = 0; q < P; ++q) {
-      double s = 0.0;
-      for (int i = 0; i < p; ++i) s += x[i] * pl.W[i * P + q];
-      A[(size_t)t * P + q] = (float)s;
-    }
-  }
+  std::vector<float> A;
+  whiten_calendar(X, n_rows, p, t_fit, pl.W, &pl.kept_mask, A);
   std::vector<float> a4((size_t)4 * pl.n_rows_pad * 4, 0.f);
   for (int32_t t = 0; t < n_rows; ++t)
     for (int q = 0; q < P; ++q) a4[(((size_t)(q >> 2) * pl.n_rows_pad) + t) * 4 + (q & 3)] = A[(size_t)t * P + q];
@@ -710,6 +750,205 @@ int mmf_fit_forecast_int(mmf_ctx* ctx, const void* y, int32_t dtype, int64_t n, 
                          mmf_stats* stats) {
   if (dtype == MMF_DT_F32) return fail(MMF_E_INVALID, "mmf_fit_forecast_int takes MMF_DT_I16 / U16 / I32; use mmf_fit_forecast_f32");
   return fit_forecast_impl(ctx, y, dtype, n, ld_y, pred_start, n_pred, out_pred, ld_out, out_beta, out_status, stats);
+}
+
+
+// ---- ragged batches: many calendars, one launch ------------------------------------------------------------------
+int mmf_plan_calendars(mmf_ctx* ctx, const double* X_all, int32_t n_cal, const int32_t* n_rows, const int32_t* t_fit,
+                       const int32_t* pred_start, int32_t n_pred, int32_t p, int32_t has_constant) {
+  if (!ctx || !X_all || !n_rows || !t_fit || !pred_start) return fail(MMF_E_INVALID, "NULL argument");
+  if (n_cal < 1 || n_cal > 65535) return fail(MMF_E_INVALID, "n_cal=%d outside [1,65535]", n_cal);
+  if (p < 1 || p > P) return fail(MMF_E_INVALID, "p=%d outside [1,%d]", p, P);
+  if (n_pred < 1 || n_pred > 64) return fail(MMF_E_UNSUPPORTED, "ragged batches forecast 1..64 rows per series (n_pred=%d)", n_pred);
+  if (ctx->pinned > 0) return fail(MMF_E_UNSUPPORTED, "a captured CUDA graph pins this context");
+  size_t total_rows = 0;
+  int32_t tmax = 0, tmin = INT32_MAX;
+  for (int c = 0; c < n_cal; ++c) {
+    if (t_fit[c] < 33 || t_fit[c] > 65535 || n_rows[c] < t_fit[c])
+      return fail(MMF_E_UNSUPPORTED, "calendar %d: need 33 <= t_fit <= 65535 and n_rows >= t_fit (t_fit=%d n_rows=%d)", c, t_fit[c], n_rows[c]);
+    if (pred_start[c] < 0 || pred_start[c] + n_pred > n_rows[c])
+      return fail(MMF_E_INVALID, "calendar %d: prediction rows [%d,%d) outside its %d design rows", c, pred_start[c],
+                  pred_start[c] + n_pred, n_rows[c]);
+    total_rows += (size_t)n_rows[c];
+    tmax = std::max(tmax, t_fit[c]);
+    tmin = std::min(tmin, t_fit[c]);
+  }
+  for (size_t i = 0; i < total_rows * (size_t)p; ++i)
+    if (!std::isfinite(X_all[i])) return fail(MMF_E_INVALID, "design matrix has a non-finite entry at %zu", i);
+  CU_TRY(cudaSetDevice(ctx->device));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  free_multi(ctx->multi);
+  MultiPlan& m = ctx->multi;
+  m.n_cal = n_cal; m.n_pred = n_pred; m.has_constant = has_constant ? 1 : 0;
+  m.t_fit_max = tmax; m.t_pad_max = (tmax + 31) & ~31; m.min_chunks = (tmin + 31) / 32;
+  m.cals.resize(n_cal);
+  m.a4_off.resize(n_cal);
+  std::vector<float> at((size_t)n_cal * 2 * P * m.t_pad_max, 0.f), apred(total_rows * P);
+  size_t a4_total = 0;
+  for (int c = 0; c < n_cal; ++c) { m.a4_off[c] = a4_total; a4_total += (size_t)4 * ((n_rows[c] + 31) & ~31); }
+  std::vector<float> a4(a4_total * 4, 0.f);
+  size_t row_off = 0;
+  std::vector<float> A;
+  double W[P * P];
+  for (int c = 0; c < n_cal; ++c) {
+    const double* X = X_all + row_off * (size_t)p;
+    if (has_constant)
+      for (int32_t t = 0; t < n_rows[c]; ++t)
+        if (X[(size_t)t * p] != 1.0) return fail(MMF_E_INVALID, "has_constant=1 but calendar %d has X[%d,0] != 1", c, t);
+    CalMeta& cm = m.cals[c];
+    whiten_calendar(X, n_rows[c], p, t_fit[c], W, &cm.kept_mask, A);
+    cm.t_fit = t_fit[c]; cm.n_chunks = (t_fit[c] + 31) / 32; cm.n_rows = n_rows[c];
+    cm.row_off = (int32_t)row_off; cm.pred_start = pred_start[c]; cm.n_pred = n_pred; cm.n_rows_pad = (n_rows[c] + 31) & ~31;
+    memcpy(apred.data() + row_off * P, A.data(), A.size() * sizeof(float));
+    float* atc = at.data() + (size_t)c * 2 * P * m.t_pad_max;
+    for (int32_t t = 0; t < t_fit[c]; ++t)
+      for (int q = 0; q < P; ++q) split_tf32(A[(size_t)t * P + q], atc + (size_t)q * m.t_pad_max + t, atc + (size_t)(P + q) * m.t_pad_max + t);
+    float* a4c = a4.data() + m.a4_off[c] * 4;
+    for (int32_t t = 0; t < n_rows[c]; ++t)
+      for (int q = 0; q < P; ++q) a4c[(((size_t)(q >> 2) * cm.n_rows_pad) + t) * 4 + (q & 3)] = A[(size_t)t * P + q];
+    row_off += (size_t)n_rows[c];
+  }
+  if (row_off > (size_t)INT32_MAX) return fail(MMF_E_UNSUPPORTED, "too many design rows in one ragged plan");
+  CU_TRY(cudaMalloc(&m.d_cals, (size_t)n_cal * sizeof(CalMeta)));
+  CU_TRY(cudaMalloc(&m.d_at, at.size() * sizeof(float)));
+  CU_TRY(cudaMalloc(&m.d_apred, apred.size() * sizeof(float)));
+  CU_TRY(cudaMalloc(&m.d_a4, a4.size() * sizeof(float)));
+  CU_TRY(cudaMalloc(&m.d_w, P * P * sizeof(float)));
+  CU_TRY(cudaMalloc(&m.d_pending_by_cal, (size_t)n_cal * sizeof(uint32_t)));
+  CU_TRY(cudaMalloc(&m.d_tmaps_y, (size_t)n_cal * 128));
+  CU_TRY(cudaMemcpy(m.d_cals, m.cals.data(), (size_t)n_cal * sizeof(CalMeta), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(m.d_at, at.data(), at.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(m.d_apred, apred.data(), apred.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(m.d_a4, a4.data(), a4.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemset(m.d_w, 0, P * P * sizeof(float)));
+  int rc = encode_2d(m.tmap_at, m.d_at, (uint64_t)m.t_pad_max, (uint64_t)n_cal * 2 * P, (uint64_t)m.t_pad_max * 4, 32, 2 * P);
+  if (rc != MMF_OK) return rc;
+  m.valid = true;
+  return MMF_OK;
+}
+
+int mmf_fit_forecast_ragged_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, const int64_t* cal_row_start,
+                                float* out_pred, int64_t ld_out, int32_t* out_status, mmf_stats* stats) {
+  if (!ctx) return fail(MMF_E_INVALID, "ctx is NULL");
+  GrowScope grow_scope(ctx);
+  MultiPlan& m = ctx->multi;
+  if (!m.valid) return fail(MMF_E_NOPLAN, "mmf_plan_calendars has not been called");
+  if (n < 0 || !cal_row_start || (n > 0 && (!y || !out_pred))) return fail(MMF_E_INVALID, "bad y / out_pred / cal_row_start / n");
+  if (cal_row_start[0] != 0 || cal_row_start[m.n_cal] != n) return fail(MMF_E_INVALID, "cal_row_start must run from 0 to n");
+  for (int c = 0; c < m.n_cal; ++c)
+    if (cal_row_start[c + 1] < cal_row_start[c]) return fail(MMF_E_INVALID, "cal_row_start must be non-decreasing");
+  if (ld_y < m.t_fit_max) return fail(MMF_E_INVALID, "ld_y=%lld < the longest calendar's t_fit=%d", (long long)ld_y, m.t_fit_max);
+  if (ld_out != m.n_pred) return fail(MMF_E_INVALID, "ragged batches write a dense [n, n_pred] table (ld_out must equal n_pred=%d)", m.n_pred);
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (n == 0) return MMF_OK;
+  if (n > (int64_t)0x7fffffff - 128) return fail(MMF_E_UNSUPPORTED, "n too large for 32-bit TMA coordinates");
+  CU_TRY(cudaSetDevice(ctx->device));
+  if (!is_device_ptr(y) || !is_device_ptr(out_pred) || (out_status && !is_device_ptr(out_status)))
+    return fail(MMF_E_INVALID, "the ragged entry point takes device buffers only");
+  if (ld_y % 4 != 0 || (reinterpret_cast<uintptr_t>(y) & 15u) != 0 || (reinterpret_cast<uintptr_t>(out_pred) & 15u) != 0)
+    return fail(MMF_E_UNSUPPORTED, "ragged batches need 16-B aligned y / out_pred and ld_y %% 4 == 0 (TMA)");
+  cudaStream_t s = ctx->stream;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  CU_TRY(cudaStreamIsCapturing(s, &cap));
+  if (cap != cudaStreamCaptureStatusNone) return fail(MMF_E_UNSUPPORTED, "ragged batches cannot be captured into a CUDA graph");
+  int32_t* status = out_status;
+  if (!status) {
+    int rc = grow_status_scratch(ctx, n, s);
+    if (rc != MMF_OK) return rc;
+    status = ctx->d_status_scratch;
+  }
+  // ---- per-call tables: tiles of 128 rows inside one calendar, the y buffer clipped at every calendar's t_fit
+  const bool same = m.key_y == y && m.key_n == n && m.key_ld == ld_y && m.key_rows.size() == (size_t)m.n_cal + 1 &&
+                    memcmp(m.key_rows.data(), cal_row_start, sizeof(int64_t) * ((size_t)m.n_cal + 1)) == 0;
+  if (!same) {
+    std::vector<TileRec> tiles;
+    tiles.reserve((size_t)(n / 128 + m.n_cal + 1));
+    for (int c = 0; c < m.n_cal; ++c)
+      for (int64_t r = cal_row_start[c]; r < cal_row_start[c + 1]; r += 128)
+        tiles.push_back(TileRec{(int32_t)r, (int32_t)std::min<int64_t>(128, cal_row_start[c + 1] - r), c, m.cals[c].n_chunks});
+    int rc = grow((void**)&m.d_tiles, &m.tiles_cap, tiles.size() * sizeof(TileRec));
+    if (rc != MMF_OK) return rc;
+    std::vector<unsigned char> maps((size_t)m.n_cal * 128);
+    for (int c = 0; c < m.n_cal; ++c) {
+      rc = encode_2d(maps.data() + (size_t)c * 128, y, (uint64_t)m.cals[c].t_fit, (uint64_t)n, (uint64_t)ld_y * 4, 32, 128);
+      if (rc != MMF_OK) return rc;
+    }
+    CU_TRY(cudaStreamSynchronize(s));                      // a previous call may still read the old tables
+    CU_TRY(cudaMemcpy(m.d_tiles, tiles.data(), tiles.size() * sizeof(TileRec), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(m.d_tmaps_y, maps.data(), maps.size(), cudaMemcpyHostToDevice));
+    m.n_tiles = (int32_t)tiles.size();
+    m.key_y = y; m.key_n = n; m.key_ld = ld_y;
+    m.key_rows.assign(cal_row_start, cal_row_start + m.n_cal + 1);
+  }
+  // ---- scratch, counters
+  const bool may_mask = !ctx->cfg.assume_finite;
+  FitArgs a{};
+  a.y = y; a.n = n; a.ld_y = ld_y; a.pred_start = 0; a.n_pred = m.n_pred; a.out = out_pred; a.ld_out = ld_out;
+  a.status = status; a.n_out = 1;
+  if (may_mask) {
+    int rc = grow((void**)&ctx->d_recs, &ctx->recs_cap_bytes, (size_t)n * sizeof(SolveRec));
+    if (rc == MMF_OK) rc = grow((void**)&ctx->d_rec_rows, &ctx->rec_rows_cap_bytes, (size_t)n * sizeof(int64_t));
+    if (rc != MMF_OK) return rc;
+    a.recs = ctx->d_recs; a.rec_rows = ctx->d_rec_rows; a.rec_cap = (uint32_t)n;
+  }
+  const int cs = ctx->counter_set;
+  uint32_t* counters = ctx->d_pending + 2 * cs;
+  ctx->set_clean[cs] = false;
+  CU_TRY(cudaMemsetAsync(counters, 0, 2 * sizeof(uint32_t), s));
+  CU_TRY(cudaMemsetAsync(m.d_pending_by_cal, 0, (size_t)m.n_cal * sizeof(uint32_t), s));
+  if (may_mask) a.rec_count = counters + 1;
+  DesignView d{};
+  d.a4 = m.d_a4; d.at = m.d_at; d.apred = m.d_apred; d.w = m.d_w;
+  d.n_rows = m.cals[0].n_rows; d.n_rows_pad = m.cals[0].n_rows_pad;
+  d.t_fit = m.t_fit_max; d.t_pad = m.t_pad_max; d.kept_mask = 0xFFFFu; d.has_constant = m.has_constant;
+  MultiView mv{};
+  mv.cals = m.d_cals; mv.tiles = m.d_tiles; mv.tmaps_y = m.d_tmaps_y; mv.pending_by_cal = m.d_pending_by_cal;
+  mv.n_cal = m.n_cal; mv.n_tiles = m.n_tiles;
+  TcLaunch tl;
+  int rc = encode_2d(tl.tmap_y, y, (uint64_t)m.cals[0].t_fit, (uint64_t)n, (uint64_t)ld_y * 4, 32, 128);   // unused by ragged tiles
+  if (rc != MMF_OK) return rc;
+  memcpy(tl.tmap_at, m.tmap_at, 128);
+  if (stats) CU_TRY(cudaEventRecord(ctx->ev_k0, s));
+  int launches = 0;
+  CU_TRY(launch_fit_tc(d, a, tl, counters, ctx->sm_count, s, 0, &mv));
+  ++launches;
+  uint32_t pend = 0;
+  if (may_mask) {
+    // rows the streaming pass could not finish (first 8 values missing, too many gaps): the general pass runs once
+    // per calendar that has any -- the one host round trip of a ragged call
+    CU_TRY(cudaMemcpyAsync(&pend, counters, sizeof(pend), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    if (pend > 0) {
+      std::vector<uint32_t> by_cal(m.n_cal);
+      CU_TRY(cudaMemcpy(by_cal.data(), m.d_pending_by_cal, (size_t)m.n_cal * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      for (int c = 0; c < m.n_cal; ++c) {
+        if (by_cal[c] == 0) continue;
+        const CalMeta& cm = m.cals[c];
+        const int64_t r0 = cal_row_start[c], nr = cal_row_start[c + 1] - r0;
+        DesignView dc = d;
+        dc.a4 = m.d_a4 + m.a4_off[c]; dc.apred = m.d_apred + (size_t)cm.row_off * P;
+        dc.n_rows = cm.n_rows; dc.n_rows_pad = cm.n_rows_pad; dc.t_fit = cm.t_fit; dc.t_pad = (cm.t_fit + 31) & ~31;
+        dc.kept_mask = cm.kept_mask;
+        FitArgs ac = a;
+        ac.y = y + r0 * ld_y; ac.n = nr; ac.out = out_pred + r0 * ld_out; ac.status = status + r0;
+        ac.pred_start = cm.pred_start; ac.recs = a.recs + r0; ac.row_base = r0; ac.cal_id = c;
+        ac.only_pending = 1; ac.pending_count = nullptr;
+        CU_TRY(launch_fit_warp(dc, ac, ctx->sm_count, s));
+        ++launches;
+      }
+    }
+    CU_TRY(launch_solve_rows(d, a, ctx->sm_count, s, m.d_cals));
+    ++launches;
+  }
+  ctx->last_set = cs;
+  if (stats) {
+    CU_TRY(cudaEventRecord(ctx->ev_k1, s));
+    CU_TRY(cudaEventSynchronize(ctx->ev_k1));
+    CU_TRY(cudaEventElapsedTime(&stats->kernel_ms, ctx->ev_k0, ctx->ev_k1));
+    stats->total_ms = stats->kernel_ms;
+    stats->n_series = n; stats->n_pending = pend; stats->kernel_launches = launches; stats->kernel_used = MMF_KERNEL_TC;
+  }
+  return MMF_OK;
 }
 
 int mmf_fit_forecast_bcast_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, int32_t pred_start,

@@ -28,6 +28,37 @@ struct DesignView {
   int32_t has_constant;
 };
 
+// ---- ragged batches: groups on MANY calendars in one launch ---------------------------------------------
+// The reference re-indexes every group on its own calendar (02:422-423); a batch can therefore hold groups with
+// different first dates and lengths.  A ragged plan stacks the whitened designs of all calendars (A operand rows,
+// prediction rows) and a launch carries a table of 128-row tiles, each inside one calendar: the kernels read the
+// tile's calendar from the table instead of from launch constants.
+struct CalMeta {                           // one calendar of a ragged plan (32 B)
+  int32_t t_fit;
+  int32_t n_chunks;                        // ceil(t_fit / 32): 32-step chunks of the tcgen05 kernel
+  int32_t n_rows;                          // design rows planned (fit + forecast rows)
+  uint32_t kept_mask;                      // whitened columns retained on this calendar
+  int32_t row_off;                         // first row of this calendar in the stacked apred / ap_hi / ap_lo / a4 tables
+  int32_t pred_start;                      // first prediction row, relative to the calendar's own rows
+  int32_t n_pred;                          // prediction rows
+  int32_t n_rows_pad;                      // rows of this calendar's a4 block (multiple of 32)
+};
+static_assert(sizeof(CalMeta) == 32, "CalMeta is two 16-B loads");
+struct TileRec {                           // one 128-row tile of a ragged launch (16 B)
+  int32_t row0;                            // first series row
+  int32_t nrows;                           // rows of the tile that belong to the calendar (1..128)
+  int32_t cal;
+  int32_t n_chunks;                        // == cals[cal].n_chunks
+};
+struct MultiView {                         // all null / 0 for an ordinary single-calendar launch
+  const CalMeta* cals;
+  const TileRec* tiles;
+  const unsigned char* tmaps_y;            // [n_cal][128]: the y buffer clipped at each calendar's t_fit (CUtensorMap)
+  uint32_t* pending_by_cal;                // [n_cal]: rows per calendar the fast path left to the general pass
+  int32_t n_cal;
+  int32_t n_tiles;
+};
+
 // One series with gaps, handed to the thread-per-series solve kernel (256 B, indexed by row).
 // Missing grid positions come in two segments so that two producers (the two transform groups of the
 // tcgen05 kernel) can append without atomics: segment g holds nm[g] entries at miss_t[g*SOLVE_SEG ...].
@@ -39,7 +70,8 @@ struct SolveRec {
   float c;                                 // centring constant
   uint16_t nm[2];                          // entries in each segment
   uint16_t miss_t[SOLVE_MISS_CAP];         // grid positions of the missing fit rows (byte offset 72)
-  uint16_t pad_[4];
+  int32_t cal;                             // ragged launches: the series' calendar (index into MultiView::cals)
+  uint16_t pad_[2];
 };
 static_assert(sizeof(SolveRec) == 256, "SolveRec is one 256-B record");
 static_assert(SOLVE_SEG % 4 == 0 && offsetof(SolveRec, miss_t) % 8 == 0, "position groups are aligned 8-B words");
@@ -70,6 +102,8 @@ struct FitArgs {
   int32_t only_pending;     // 1: process only rows whose status == MMF_STATUS_PENDING
   const uint32_t* pending_count;  // nullable; if non-null and *pending_count == 0 the kernel exits at once
   uint32_t* zero_next;      // nullable: 2 counters of the NEXT call's set, zeroed by the tcgen05 kernel (no memset node)
+  int64_t row_base;         // ragged fallback launches cover one calendar's rows: absolute row of this launch's row 0
+  int32_t cal_id;           //   ... and that calendar's index (written into the records the launch queues)
 };
 
 // warp-per-series CUDA-core kernel (general path)
@@ -78,7 +112,8 @@ size_t fit_warp_smem_bytes(const DesignView& d, int* smem_rows);
 
 // thread-per-series normal equations for the deferred masked rows: Gram downdate, in-order Cholesky with
 // pivot dropping and both triangular solves entirely in registers, then the forecasts
-cudaError_t launch_solve_rows(const DesignView& d, const FitArgs& a, int sm_count, cudaStream_t s);
+cudaError_t launch_solve_rows(const DesignView& d, const FitArgs& a, int sm_count, cudaStream_t s,
+                              const CalMeta* cals = nullptr);
 
 // fitted values + forecasts for MANY prediction rows (the reference's "Demand_Fitted for every date"
 // contract, 02:484-494): out[n, n_pred] = c + gamma A_pred^T as a tcgen05 GEMM with TMA-stored tiles
@@ -97,7 +132,8 @@ struct TcLaunch {
 };
 // variant: 0 = automatic, 1 = <10 smem stages, 1 forecast staging tile>, 2 = <8 stages, 2 staging tiles>
 cudaError_t launch_fit_tc(const DesignView& d, const FitArgs& a, const TcLaunch& tl,
-                          uint32_t* pending_count, int sm_count, cudaStream_t s, int variant = 0);
+                          uint32_t* pending_count, int sm_count, cudaStream_t s, int variant = 0,
+                          const MultiView* multi = nullptr);
 bool fit_tc_supported(const DesignView& d, const FitArgs& a, const char** why);
 
 // per-series model selection by hold-out MSE over nested whitened designs (select.cu)

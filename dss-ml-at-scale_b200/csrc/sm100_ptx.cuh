@@ -61,6 +61,11 @@ constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
 __device__ __forceinline__ void prefetch_tensormap(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
+// A tensor map that lives in GLOBAL memory (written by the host before the launch, e.g. one map per calendar of a
+// ragged batch) must be acquired by the tensormap proxy before its first use in a TMA instruction.
+__device__ __forceinline__ void fence_tensormap_acquire(const void* tmap) {
+  asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
 // 2-D tiled load global -> shared, completion on an mbarrier (complete_tx::bytes)
 __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tmap, uint32_t bar,
                                             int32_t c0, int32_t c1, uint64_t hint) {

@@ -24,8 +24,9 @@ __device__ __forceinline__ void prefetch_rec(const SolveRec* r) {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(r) + 128));
 }
 
+template <bool MULTI>
 __global__ void __launch_bounds__(THREADS, 2)
-solve_rows_kernel(const DesignView d, const FitArgs a) {
+solve_rows_kernel(const DesignView d0, const FitArgs a, const CalMeta* __restrict__ cals) {
   asm volatile("griddepcontrol.wait;" ::: "memory");    // programmatic dependent launch: the producer kernels are done
   const uint32_t count = min(*a.rec_count, a.rec_cap);
   const uint32_t stride = gridDim.x * THREADS;
@@ -52,6 +53,17 @@ solve_rows_kernel(const DesignView d, const FitArgs a) {
     }
     const float c = rec.c;
     const int nm0 = rec.nm[0], nm1 = rec.nm[1];
+    // ragged launches: the record names its calendar; the stacked design tables are indexed from that calendar's row 0
+    DesignView d = d0;
+    int pred_start = a.pred_start;
+    if (MULTI) {
+      const int4* cp = reinterpret_cast<const int4*>(cals + rec.cal);
+      const int4 m0 = __ldg(cp), m1 = __ldg(cp + 1);
+      d.t_fit = m0.x;
+      d.kept_mask = static_cast<uint32_t>(m0.w);
+      d.apred = d0.apred + (size_t)m1.x * P;
+      pred_start = m1.y;
+    }
 
     // ---- G_i = I - sum over the missing rows of a_t a_t^T, Cholesky with pivot dropping, both solves (solve_math.cuh)
     const unsigned dropped = masked_solve(d, b, nm0, nm1, [&](int seg, int gi) {
@@ -67,7 +79,7 @@ solve_rows_kernel(const DesignView d, const FitArgs a) {
     // ---- forecasts (16-B stores when the table allows it: a thread owns a whole row of it)
     const int64_t off = row * a.ld_out;
     auto predict = [&](int k) -> float {
-      const float4* ap = reinterpret_cast<const float4*>(d.apred + (size_t)(a.pred_start + k) * P);
+      const float4* ap = reinterpret_cast<const float4*>(d.apred + (size_t)(pred_start + k) * P);
       const float4 a0 = __ldg(ap), a1 = __ldg(ap + 1), a2 = __ldg(ap + 2), a3 = __ldg(ap + 3);
       float s = c;
       s = fmaf(a0.x, b[0], s);  s = fmaf(a0.y, b[1], s);  s = fmaf(a0.z, b[2], s);  s = fmaf(a0.w, b[3], s);
@@ -100,7 +112,7 @@ solve_rows_kernel(const DesignView d, const FitArgs a) {
 
 }  // namespace
 
-cudaError_t launch_solve_rows(const DesignView& d, const FitArgs& a, int sm_count, cudaStream_t s) {
+cudaError_t launch_solve_rows(const DesignView& d, const FitArgs& a, int sm_count, cudaStream_t s, const CalMeta* cals) {
   if (a.recs == nullptr || a.rec_cap == 0) return cudaSuccess;
   const int64_t want = ((int64_t)a.rec_cap + THREADS - 1) / THREADS;
   const int64_t cap = (int64_t)sm_count * 8;
@@ -115,7 +127,8 @@ cudaError_t launch_solve_rows(const DesignView& d, const FitArgs& a, int sm_coun
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, solve_rows_kernel, d, a);
+  return cals != nullptr ? cudaLaunchKernelEx(&cfg, solve_rows_kernel<true>, d, a, cals)
+                         : cudaLaunchKernelEx(&cfg, solve_rows_kernel<false>, d, a, cals);
 }
 
 }  // namespace mmf

@@ -234,6 +234,65 @@ class ForecastEngine:
         self._calendar_plan = (days[pred_start:pred_start + n_pred], pred_start, n_pred)
         return self._calendar_plan
 
+    # ---- ragged batches: many calendars, one launch ----------------------------------------------
+    def plan_calendars(self, starts, t_lens, freq: str = "D", horizon: int = 28, design: str = "trend_season_exog"):
+        """Plan ALL calendars of a ragged batch (future mode): calendar ``c`` starts at ``starts[c]`` and has
+        ``t_lens[c]`` grid rows; every series is fit on its whole history and forecast ``horizon`` rows past its end.
+        One host call whitens every calendar (``mmf_plan_calendars``); ``fit_forecast_ragged`` then fits all groups
+        in one kernel pass.  Returns the forecast dates per calendar, ``[n_cal, horizon]`` datetime64[D]."""
+        starts = [np.datetime64(s, "D") for s in starts]
+        t_lens = [int(t) for t in t_lens]
+        if len(starts) != len(t_lens) or not starts:
+            raise ValueError("starts and t_lens must have the same non-zero length")
+        blocks, dates = [], []
+        for st, tl in zip(starts, t_lens):
+            days = D.calendar_grid(st, tl + horizon, freq)
+            blocks.append(D.design_matrix(days, tl, design))
+            dates.append(np.asarray(days[tl:tl + horizon], dtype="datetime64[D]"))
+        X = np.ascontiguousarray(np.concatenate(blocks, axis=0), dtype=np.float64)
+        n_rows = np.array([tl + horizon for tl in t_lens], dtype=np.int32)
+        t_fit = np.array(t_lens, dtype=np.int32)
+        N.check(self._lib.mmf_plan_calendars(self._h, X.ctypes.data, len(starts), n_rows.ctypes.data, t_fit.ctypes.data,
+                                             t_fit.ctypes.data, int(horizon), X.shape[1],
+                                             1 if D.design_has_constant(design) else 0))
+        self._ragged = (len(starts), int(horizon), int(max(t_lens)))
+        return np.stack(dates)
+
+    def fit_forecast_ragged(self, y, cal_row_start, out=None, status=None, want_status: bool = False,
+                            want_stats: bool = False):
+        """Fit a ragged batch: ``y`` [n, ld] float32 CUDA tensor whose rows are grouped by calendar -- calendar ``c``
+        owns rows ``[cal_row_start[c], cal_row_start[c+1])`` and reads columns ``[0, t_len_c)`` of them.  Returns the
+        dense ``[n, horizon]`` forecast table (or a dict with ``status`` / ``stats``)."""
+        import torch
+        if getattr(self, "_ragged", None) is None:
+            raise RuntimeError("plan_calendars() must be called first")
+        n_cal, horizon, t_max = self._ragged
+        yp, n, t_have, ld_y = _describe(y, "y")
+        if not (_is_torch(y) and y.is_cuda and y.dtype == torch.float32) or t_have < t_max:
+            raise ValueError(f"y must be a float32 CUDA tensor with at least {t_max} columns")
+        rows = np.ascontiguousarray(cal_row_start, dtype=np.int64)
+        if rows.shape != (n_cal + 1,):
+            raise ValueError("cal_row_start needs n_cal + 1 entries")
+        self.set_stream(torch.cuda.current_stream(y.device).cuda_stream)
+        if out is None:
+            out = torch.empty((n, horizon), device=y.device, dtype=torch.float32)
+        if want_status and status is None:
+            status = torch.empty(n, device=y.device, dtype=torch.int32)
+        st = N.MmfStats() if want_stats else None
+        N.check(self._lib.mmf_fit_forecast_ragged_f32(self._h, yp, n, ld_y, rows.ctypes.data, out.data_ptr(), out.stride(0),
+                                                      status.data_ptr() if status is not None else None,
+                                                      C.byref(st) if st is not None else None))
+        if not (want_status or want_stats):
+            return out
+        res = {"pred": out}
+        if status is not None:
+            res["status"] = status
+        if st is not None:
+            self.launches += st.kernel_launches
+            res["stats"] = Stats(st.kernel_ms, st.total_ms, st.n_series, st.n_pending, st.h2d_bytes, st.d2h_bytes,
+                                 st.kernel_launches, "tc")
+        return res
+
     def whitening(self):
         W = np.zeros((N.MMF_P, N.MMF_P), dtype=np.float64)
         kept = np.zeros(N.MMF_P, dtype=np.int32)

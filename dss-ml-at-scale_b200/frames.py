@@ -292,8 +292,35 @@ def pack_table_host(table, keys=DEFAULT_KEYS, date_col="Date", value_col="Demand
 
 
 # ---- the drop-in UDF ---------------------------------------------------------------------------
+RAGGED_MIN_BUCKETS = 2        # from this many calendars on, future-mode batches go through ONE ragged launch
+
+
+def _fit_buckets_ragged(buckets, eng, freq, horizon, design, on_device):
+    """All calendars of the batch in one launch (``mmf_plan_calendars`` + ``mmf_fit_forecast_ragged_f32``): the groups'
+    rows are laid out calendar after calendar in one device buffer, each calendar's design is whitened in the same
+    host call, and one pass of the tcgen05 kernel fits every group against its own calendar (02:422-423 per group)."""
+    import torch
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t_max = max(b.t_len for b in buckets)
+    rows = np.cumsum([0] + [b.y.shape[0] for b in buckets]).astype(np.int64)
+    y = torch.zeros((int(rows[-1]), (t_max + 3) & ~3), dtype=torch.float32, device=dev)
+    for i, b in enumerate(buckets):
+        src = b.y if on_device else torch.from_numpy(b.y)
+        y[int(rows[i]):int(rows[i + 1]), :b.t_len].copy_(src, non_blocking=True)
+    dates = eng.plan_calendars([b.start for b in buckets], [b.t_len for b in buckets], freq, horizon, design)
+    pred = eng.fit_forecast_ragged(y, rows).cpu().numpy()
+    for i, b in enumerate(buckets):
+        y_host = b.y.cpu().numpy() if on_device else b.y
+        yield b, dates[i], horizon, y_host, pred[int(rows[i]):int(rows[i + 1])]
+
+
 def _fit_buckets(buckets, eng, freq, horizon, mode, design, select, on_device):
     """Run the engine over every bucket: yields (bucket, out_days, n_pred, y_host, pred_host)."""
+    if (mode == "future" and select is None and len(buckets) >= RAGGED_MIN_BUCKETS and 1 <= horizon <= 64
+            and hasattr(eng, "fit_forecast_ragged") and all(33 <= b.t_len <= 65535 for b in buckets)):
+        yield from _fit_buckets_ragged(buckets, eng, freq, horizon, design, on_device)
+        return
     for b in buckets:
         out_days, pred_start, n_pred = eng.plan_calendar(b.start, b.t_len, freq, horizon, mode, design)
         if select is not None:

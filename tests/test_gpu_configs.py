@@ -328,3 +328,107 @@ def test_integer_ingest_is_bit_equal_to_float32_ingest(dtype):
     with pytest.raises(ValueError):
         mmf.to_integer_demand(y + 0.5, dtype)
     eng.close()
+
+
+# ---- ragged batches: groups on many calendars, ONE launch ---------------------------------------------------------
+def _ragged_case(seed=0):
+    """Calendars with different first dates AND lengths, group counts around the 128-row tile edge, rows with gaps,
+    rows the streaming pass must hand to the general pass, an empty row; columns beyond a row's own length hold NaN
+    on purpose (the per-calendar tensor maps must clip them away)."""
+    import datetime as dt
+    rng = np.random.default_rng(seed)
+    cals = [(dt.date(2019, 1, 1), 400, 300), (dt.date(2019, 3, 5), 333, 127), (dt.date(2018, 7, 9), 365, 128),
+            (dt.date(2020, 2, 1), 97, 129), (dt.date(2019, 1, 2), 400, 1), (dt.date(2017, 12, 25), 64, 5),
+            (dt.date(2019, 6, 30), 250, 700)]
+    t_max = max(t for _, t, _ in cals)
+    ld = (t_max + 3) & ~3
+    blocks, rows = [], [0]
+    for ci, (start, t, n) in enumerate(cals):
+        yb, _ = mmf.synth.daily_store_item_demand(n, t, seed=1000 + ci, end=np.datetime64(start) + np.timedelta64(t - 1, "D"))
+        full = np.full((n, ld), np.nan, dtype=np.float32)
+        full[:, :t] = yb
+        if n >= 5:
+            full[1, 10:25] = np.nan                           # in-stream gap path
+            full[2, :9] = np.nan                              # first values missing: general pass (per-calendar launch)
+            full[3, :t] = np.nan                              # empty
+            full[4, rng.choice(np.arange(1, t), size=min(60, t // 3), replace=False)] = np.nan
+        blocks.append(full)
+        rows.append(rows[-1] + n)
+    return cals, np.concatenate(blocks), np.array(rows, dtype=np.int64), ld
+
+
+def test_ragged_calendars_one_launch_matches_oracle_and_per_bucket_calls():
+    import torch
+    h = 28
+    cals, y, rows, ld = _ragged_case()
+    eng = mmf.ForecastEngine()
+    dates = eng.plan_calendars([c[0] for c in cals], [c[1] for c in cals], "D", h)
+    assert dates.shape == (len(cals), h)
+    yd = torch.from_numpy(y).cuda()
+    res = eng.fit_forecast_ragged(yd, rows, want_status=True, want_stats=True)
+    torch.cuda.synchronize()
+    pred, status = res["pred"].cpu().numpy(), res["status"].cpu().numpy()
+    assert res["stats"].n_pending >= sum(1 for c in cals if c[2] >= 5)          # the leading-gap rows
+    eng1 = mmf.ForecastEngine()
+    for ci, (start, t, n) in enumerate(cals):
+        r0, r1 = int(rows[ci]), int(rows[ci + 1])
+        yb = y[r0:r1, :t]
+        grid = O.calendar_grid(start, t + h, "D")
+        want, wst, _, ratio = O.fit_forecast_packed(yb, O.design_matrix(grid, t), t, t, h, return_gamma=True)
+        assert np.array_equal(status[r0:r1], wst), ci
+        assert str(dates[ci][0]) == str(np.datetime64(start) + np.timedelta64(t, "D"))
+        ok = wst != 1
+        assert np.isnan(pred[r0:r1][~ok]).all()
+        from conftest import forecast_leverage
+        lev = forecast_leverage(O.design_matrix(grid, t), t, t, h)
+        tol = tolerance(yb, lev) / np.minimum(1.0, ratio[ok] / 0.25)
+        rel = np.abs(pred[r0:r1][ok] - want[ok]).max(axis=1) / tol
+        _le(rel.max(), 1.0, f"calendar {ci}: t={t} n={n} leverage {lev:.3g}")
+        # the same rows through the single-calendar entry point: same kernel, same arithmetic per row
+        single = mmf.forecast_packed(mmf.device_packed(yb), start, "D", h, "future", engine=eng1).cpu().numpy()
+        assert np.array_equal(single, pred[r0:r1], equal_nan=True), ci
+    eng.close()
+    eng1.close()
+
+
+def test_ragged_rejects_what_it_cannot_do():
+    import torch
+    eng = mmf.ForecastEngine()
+    with pytest.raises(mmf.MmfError):
+        eng.plan_calendars(["2020-01-01"], [20], "D", 28)                        # < 33 fit rows
+    with pytest.raises(mmf.MmfError):
+        eng.plan_calendars(["2020-01-01"], [100], "D", 80)                       # > 64 forecast rows
+    eng.plan_calendars(["2020-01-01", "2020-02-01"], [100, 90], "D", 28)
+    y = torch.zeros((10, 100), device="cuda")
+    with pytest.raises(mmf.MmfError):
+        eng.fit_forecast_ragged(y, [0, 4, 9])                                    # does not end at n
+    eng.close()
+
+
+def test_forecast_groups_many_calendars_future_mode_uses_one_ragged_launch():
+    """DataFrame boundary: groups with different first dates / lengths (the reference re-grids each group on its own
+    calendar, 02:422-423) in future mode go through the ragged launch and match the per-group oracle UDF."""
+    import pandas as pd
+    rng = np.random.default_rng(3)
+    frames = []
+    for g in range(60):
+        t = int(rng.integers(40, 90))
+        start = np.datetime64("2021-01-04") + np.timedelta64(7 * int(rng.integers(0, 6)), "D")
+        days = start + np.arange(t) * np.timedelta64(7, "D")
+        vals = np.round(1000 + 5 * np.arange(t) + rng.normal(0, 20, t)).astype(np.float32)
+        keep = rng.random(t) > 0.04
+        keep[0] = keep[-1] = True
+        frames.append(pd.DataFrame({"Product": f"p{g % 5}", "SKU": f"s{g:03d}", "Date": days[keep].astype("datetime64[ns]"),
+                                    "Demand": vals[keep]}))
+    df = pd.concat(frames, ignore_index=True).sample(frac=1.0, random_state=1)
+    df["Date"] = df["Date"].dt.date
+    kw = dict(freq="W-MON", horizon=8, mode="future")
+    got = mmf.forecast_groups(df, **kw)
+    want = O.fanout_apply(df, lambda p: O.build_tune_and_score_model(p, **kw), ("Product", "SKU"))
+    assert len(got) == len(want) == 60 * 8
+    assert (got["SKU"].to_numpy() == want["SKU"].to_numpy()).all()
+    assert (got["Date"].dt.date.to_numpy() == want["Date"].to_numpy()).all()
+    err = np.abs(got["Demand_Fitted"].to_numpy() - want["Demand_Fitted"].to_numpy())
+    # weekly histories of 40-90 points extrapolated 8 weeks: leverage of a few units; scale the tolerance like the
+    # packed tests do (forecast_leverage) with a bound that holds for every calendar of this batch
+    _le(err.max(), 40 * tolerance(df["Demand"].to_numpy()), "ragged DataFrame batch vs per-group oracle UDF")
