@@ -252,11 +252,10 @@ inline void split_tf32(float v, float* hi, float* lo) {
   uint32_t lb; memcpy(&lb, &l, 4); lb &= 0xFFFFE000u; memcpy(lo, &lb, 4);
 }
 
-// Enqueue the fit for device-resident buffers on `s`.  status must be non-null.
-int run_device(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, int32_t pred_start, int32_t n_pred,
-               float* out, int64_t ld_out, float* beta, int32_t* status, cudaStream_t s, int* launches,
-               int* kernel_used, float* const* out_more = nullptr, int n_out = 1, int multimem = 0,
-               const SelectArgs* sel = nullptr) {
+// Enqueue the fit of ONE slab of device-resident rows on `s`.  status must be non-null.
+int run_device_slab(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, int32_t pred_start, int32_t n_pred,
+                    float* out, int64_t ld_out, float* beta, int32_t* status, cudaStream_t s, int* launches,
+                    int* kernel_used, float* const* out_more, int n_out, int multimem, const SelectArgs* sel) {
   const DesignView d = view_of(ctx->plan);
   FitArgs a{};
   a.y = y; a.n = n; a.ld_y = ld_y; a.pred_start = pred_start; a.n_pred = n_pred;
@@ -351,6 +350,41 @@ int run_device(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, int32_t pr
   if (!capturing) {                                       // toggle only once every launch of the call is enqueued
     ctx->set_clean[cs ^ 1] = (kernel == MMF_KERNEL_TC);   // zeroed by this call's tcgen05 kernel
     ctx->counter_set = cs ^ 1;
+  }
+  return MMF_OK;
+}
+
+// Enqueue the fit for device-resident buffers on `s`: slab by slab, so that the per-row scratch (a 256-B record and a
+// work-list entry per row for the series with gaps, gamma / c for the many-rows predict kernel) is proportional to a
+// slab, not to the batch.  One slab for batches up to a million rows; beyond that the slab is sized so the scratch
+// stays under ~5 % of the input (10 M x 365: 4 slabs, 0.7 GB instead of 2.6 GB).  Slabs run back to back on the
+// stream; the scratch of slab i is free again when slab i+1 starts (stream order).
+int run_device(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, int32_t pred_start, int32_t n_pred,
+               float* out, int64_t ld_out, float* beta, int32_t* status, cudaStream_t s, int* launches,
+               int* kernel_used, float* const* out_more = nullptr, int n_out = 1, int multimem = 0,
+               const SelectArgs* sel = nullptr) {
+  int64_t slab = n;
+  if (n > (int64_t)1 << 20) {
+    const double input_bytes = (double)n * (double)ctx->plan.t_fit * 4.0;
+    slab = std::max<int64_t>((int64_t)1 << 20, (int64_t)(0.05 * input_bytes / (double)(sizeof(SolveRec) + sizeof(int64_t))));
+    slab = std::min(n, (slab + 127) & ~(int64_t)127);                 // whole 128-row tiles
+    const int64_t n_slabs = (n + slab - 1) / slab;
+    slab = (((n + n_slabs - 1) / n_slabs) + 127) & ~(int64_t)127;     // equal slabs
+  }
+  for (int64_t off = 0; off < n; off += slab) {
+    const int64_t m = std::min(slab, n - off);
+    float* more[MAX_OUT - 1] = {};
+    for (int i = 0; i + 1 < n_out && i < MAX_OUT - 1; ++i) more[i] = out_more[i] + off * ld_out;
+    SelectArgs sel_slab;
+    if (sel != nullptr) {
+      sel_slab = *sel;
+      if (sel_slab.out_choice) sel_slab.out_choice += off;
+      if (sel_slab.out_mse) sel_slab.out_mse += off;
+    }
+    const int rc = run_device_slab(ctx, y + off * ld_y, m, ld_y, pred_start, n_pred, out + off * ld_out, ld_out,
+                                   beta ? beta + off * P : nullptr, status + off, s, launches, kernel_used, more, n_out,
+                                   multimem, sel != nullptr ? &sel_slab : nullptr);
+    if (rc != MMF_OK) return rc;
   }
   return MMF_OK;
 }

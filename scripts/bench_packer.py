@@ -50,7 +50,7 @@ def main():
         N.check(lib.mmf_pack_minmax(h, gid.data_ptr(), day.data_ptr(), n, g.value, gmin.data_ptr(), gmax.data_ptr()))
         rog = torch.arange(g.value, device="cuda", dtype=torch.int64)
         N.check(lib.mmf_pack_scatter_f32(h, gid.data_ptr(), day.data_ptr(), val.data_ptr(), n, rog.data_ptr(),
-                                         gmin.data_ptr(), 1, out.data_ptr(), g.value, out.stride(0), T))
+                                         gmin.data_ptr(), 1, out.data_ptr(), g.value, out.stride(0), T, None))
         return g.value
 
     for _ in range(2):
