@@ -33,8 +33,8 @@ using namespace sm100;
 constexpr int TILE_M = 128;            // series per tile == TMEM lanes
 constexpr int KC = 32;                 // time steps per stage == one 128-B swizzle row
 // The shared-memory ring (20 KB per stage) and the number of forecast staging tiles are template parameters of the
-// kernel: <10 stages, 1 staging tile> for a single destination, <8, 2> when the tile also goes to peer GPUs (the
-// second staging tile lets tile k+1 be assembled while the NVLink stores of tile k are still reading tile k's).
+// kernel: <10 stages, 1 staging tile> is the product configuration, <8, 2> (a second staging tile lets tile k+1 be
+// assembled while the NVLink stores of tile k are still reading tile k's) an experiment that did not pay.
 constexpr int NGROUPS = 2;             // transform groups (alternate chunks)
 constexpr int ASLOTS = MMF_TC_ASLOTS;  // TMEM A-operand slots per transform group
 constexpr int MAX_PRED = 64;           // forecast rows the epilogue supports
@@ -570,8 +570,11 @@ cudaError_t launch_fit_tc(const DesignView& d, const FitArgs& a, const TcLaunch&
   const int n_tiles = (int)((a.n + TILE_M - 1) / TILE_M);
   const int n_chunks = d.t_pad / KC;
   const MultiView none{};
-  // variant 0 = automatic: two staging tiles as soon as a tile has more than one destination
-  const bool two = variant == 2 || (variant == 0 && (a.n_out > 1 || a.out_multimem == 2));
+  // variant 0 / 1: ten stages, one staging tile.  The <8 stages, 2 staging tiles> instantiation (tile k+1 staged while
+  // the peer stores of tile k still read theirs) measured no faster at 2, 4 or 8 GPUs -- the multi-destination step
+  // is bound by HBM writes of the incoming copies (N = 4) and by NVLink ingress (N = 8), not by the staging tile
+  // (profiles/r02/multi_gpu.md) -- and 0.9 % slower on one GPU, so it is only built for experiments (variant 2).
+  const bool two = variant == 2;
   return two ? launch_variant<8, 2, false>(d, a, tl, pending_count, sm_count, s, n_tiles, n_chunks, none)
              : launch_variant<10, 1, false>(d, a, tl, pending_count, sm_count, s, n_tiles, n_chunks, none);
 }

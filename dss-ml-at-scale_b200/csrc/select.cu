@@ -37,35 +37,47 @@ select_kernel(const DesignView d, const FitArgs a, const SelectArgs sel) {
       g[4 * q] = v.x; g[4 * q + 1] = v.y; g[4 * q + 2] = v.z; g[4 * q + 3] = v.w;
     }
     const float c = a.out_c[row];
-    float sse[MMF_MAX_CAND];
+    // Running prefix sums over the whitened columns give every nested model's residual at once: after column p the
+    // partial sum IS the prediction of the model made of columns 0..p, so each held-out row costs 16 FMAs for the
+    // predictions and 16 for the squared errors of all 16 prefix lengths (statically indexed registers); the
+    // candidates' scores are picked out of those 16 at the end.  (Testing every column against every candidate
+    // inside the loop made this kernel issue-bound at ~4x the instructions: profiles/r02/ncu_select.txt.)
+    float sse[P];
 #pragma unroll
-    for (int k = 0; k < MMF_MAX_CAND; ++k) sse[k] = 0.f;
+    for (int p = 0; p < P; ++p) sse[p] = 0.f;
     int n_obs = 0;
     const float* __restrict__ yh = a.y + row * a.ld_y + d.t_fit;
     for (int t = 0; t < sel.n_hold; ++t) {
       const float y = __ldg(yh + t);
       if ((__float_as_uint(y) & 0x7f800000u) == 0x7f800000u) continue;      // missing held-out value
       ++n_obs;
-      const float* arow = s_hold + t * P;
-      float s = c;
-      int k = 0;
+      const float4* arow = reinterpret_cast<const float4*>(s_hold + t * P);
+      const float4 a0 = arow[0], a1 = arow[1], a2 = arow[2], a3 = arow[3];
+      const float av[P] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
+      float e = y - c;
 #pragma unroll
       for (int p = 0; p < P; ++p) {
-        s = fmaf(arow[p], g[p], s);
-#pragma unroll
-        for (int kk = 0; kk < MMF_MAX_CAND; ++kk)               // candidate kk ends after column cand[kk]-1
-          if (kk < sel.n_cand && sel.cand[kk] == p + 1) { const float e = y - s; sse[kk] = fmaf(e, e, sse[kk]); }
+        e = fmaf(-av[p], g[p], e);                             // residual of the model on columns 0..p
+        sse[p] = fmaf(e, e, sse[p]);
       }
-      (void)k;
     }
+    auto sse_of = [&](int m) -> float {                        // m = number of leading columns, 1..16
+      float v = sse[0];
+#pragma unroll
+      for (int p = 1; p < P; ++p) v = (m == p + 1) ? sse[p] : v;
+      return v;
+    };
     int best = sel.n_cand - 1;                                   // no observed held-out row: keep the full model
-    float best_sse = sse[best];
+    float best_sse = sse_of(sel.cand[best]);
     if (n_obs > 0) {
       best = 0;
-      best_sse = sse[0];
+      best_sse = sse_of(sel.cand[0]);
 #pragma unroll
       for (int kk = 1; kk < MMF_MAX_CAND; ++kk)
-        if (kk < sel.n_cand && sse[kk] < best_sse) { best = kk; best_sse = sse[kk]; }
+        if (kk < sel.n_cand) {
+          const float v = sse_of(sel.cand[kk]);
+          if (v < best_sse) { best = kk; best_sse = v; }
+        }
     }
     const int m = sel.cand[best];
     float4* gw = reinterpret_cast<float4*>(a.out_gamma + row * P);
