@@ -40,6 +40,8 @@ class MmfConfig(C.Structure):
         ("tc_variant", C.c_int32),
         ("chunk_series", C.c_int64),
         ("stream", C.c_void_p),
+        ("host_narrow", C.c_int32),
+        ("host_threads", C.c_int32),
     ]
 
 

@@ -12,9 +12,21 @@
 #include <string>
 #include <vector>
 
+#include <sched.h>
+#include <thread>
+
 #include "mmf_internal.cuh"
 
 using namespace mmf;
+
+// host_narrow.cpp: exact float32 -> uint16 narrowing of a chunk on a few host threads
+namespace mmf {
+class NarrowPool;
+NarrowPool* narrow_pool_create(int n_threads);
+void narrow_pool_destroy(NarrowPool* p);
+int narrow_pool_size(const NarrowPool* p);
+bool narrow_f32_to_u16(NarrowPool* p, const float* src, int64_t ld_src, uint16_t* dst, int64_t ld_dst, int64_t n, int32_t t);
+}  // namespace mmf
 
 namespace {
 
@@ -113,6 +125,7 @@ struct Staging {
   float* d_beta = nullptr;   size_t beta_cap = 0;
   int32_t* d_status = nullptr; size_t status_cap = 0;
   cudaEvent_t ev_h2d = nullptr, ev_comp = nullptr, ev_d2h = nullptr;
+  uint16_t* h_narrow = nullptr; size_t h_narrow_cap = 0;   // pinned HOST slot: the chunk narrowed to uint16 (host_narrow.cpp)
 };
 
 }  // namespace
@@ -148,6 +161,7 @@ struct mmf_ctx {
   Plan plan;
   MultiPlan multi;
   Staging st[NBUF];
+  NarrowPool* narrow_pool = nullptr;   // created on the first host-buffer call that narrows
 };
 
 namespace {
@@ -483,10 +497,12 @@ int mmf_destroy(mmf_ctx* ctx) {
   for (int i = 0; i < NBUF; ++i) {
     Staging& s = ctx->st[i];
     cudaFree(s.d_y); cudaFree(s.d_yraw); cudaFree(s.d_out); cudaFree(s.d_beta); cudaFree(s.d_status);
+    if (s.h_narrow) cudaFreeHost(s.h_narrow);
     if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
     if (s.ev_comp) cudaEventDestroy(s.ev_comp);
     if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
   }
+  if (ctx->narrow_pool) narrow_pool_destroy(ctx->narrow_pool);
   cudaFree(ctx->d_pending);
   cudaFree(ctx->d_recs);
   cudaFree(ctx->d_rec_rows);
@@ -667,13 +683,34 @@ static int fit_forecast_impl(mmf_ctx* ctx, const void* y_any, int32_t dtype, int
     const int64_t pitch = (pl.t_fit + 3) & ~3;                 // staged row pitch (floats), TMA-friendly
     const int64_t rpitch = (pl.t_fit + 7) & ~7;                // staged row pitch of an integer chunk (16-B rows)
     const int64_t opitch = (n_pred + 3) & ~3;
+    // float32 host input is narrowed to uint16 chunk by chunk on host threads while the previous chunk's copy is in
+    // flight (exact or not used: host_narrow.cpp), so half the bytes cross PCIe -- the link is what bounds this path
+    bool narrow = !is_int && !y_dev && ctx->cfg.host_narrow != 2 &&
+                  (ctx->cfg.host_narrow == 1 || n * (int64_t)pl.t_fit >= ((int64_t)4 << 20));
+    if (narrow && ctx->narrow_pool == nullptr) {
+      int want = ctx->cfg.host_threads;
+      if (want <= 0) {
+        cpu_set_t set;
+        const int have = (sched_getaffinity(0, sizeof(set), &set) == 0) ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+        want = std::max(1, std::min(24, have / 2));
+      }
+      ctx->narrow_pool = narrow_pool_create(want - 1);         // the calling thread is the last worker
+    }
     const mmf_ctx* pinned_scope = g_grow_ctx;
     g_grow_ctx = nullptr;                                       // staging slots are never part of a captured graph
     for (int i = 0; i < NBUF; ++i) {
       Staging& s = ctx->st[i];
       int rc = MMF_OK;
       if (!y_dev || is_int) rc = grow((void**)&s.d_y, &s.y_cap, (size_t)chunk * pitch * sizeof(float));
-      if (rc == MMF_OK && is_int && !y_dev) rc = grow(&s.d_yraw, &s.yraw_cap, (size_t)chunk * rpitch * esize);
+      if (rc == MMF_OK && (is_int || narrow) && !y_dev)
+        rc = grow(&s.d_yraw, &s.yraw_cap, (size_t)chunk * rpitch * (narrow ? 2 : esize));
+      if (rc == MMF_OK && narrow && s.h_narrow_cap < (size_t)chunk * rpitch * 2) {
+        if (s.h_narrow) cudaFreeHost(s.h_narrow);
+        s.h_narrow = nullptr; s.h_narrow_cap = 0;
+        if (cudaHostAlloc((void**)&s.h_narrow, (size_t)chunk * rpitch * 2, cudaHostAllocDefault) == cudaSuccess)
+          s.h_narrow_cap = (size_t)chunk * rpitch * 2;
+        else { cudaGetLastError(); narrow = false; }           // cannot pin the slot: plain float32 copies
+      }
       if (rc == MMF_OK && !o_dev) rc = grow((void**)&s.d_out, &s.out_cap, (size_t)chunk * opitch * sizeof(float));
       if (rc == MMF_OK && out_beta && !b_dev) rc = grow((void**)&s.d_beta, &s.beta_cap, (size_t)chunk * P * sizeof(float));
       if (rc == MMF_OK && (!out_status || !s_dev)) rc = grow((void**)&s.d_status, &s.status_cap, (size_t)chunk * sizeof(int32_t));
@@ -710,7 +747,21 @@ static int fit_forecast_impl(mmf_ctx* ctx, const void* y_any, int32_t dtype, int
         ++launches;
         yk = s.d_y; ldk = pitch;
       } else if (y_dev) { yk = y + off * ld_y; ldk = ld_y; }
-      else {
+      else if (narrow && [&]() -> bool {
+                 // the slot's previous copy (chunk it - NBUF) must have left the host buffer before it is rewritten
+                 if (it >= NBUF && cudaEventSynchronize(s.ev_h2d) != cudaSuccess) return false;
+                 return narrow_f32_to_u16(ctx->narrow_pool, y + off * ld_y, ld_y, s.h_narrow, rpitch, m, pl.t_fit);
+               }()) {
+        if (it >= NBUF) CU_TRY(cudaStreamWaitEvent(ctx->s_h2d, s.ev_comp, 0));     // device staging free again
+        CU_TRY(cudaMemcpyAsync(s.d_yraw, s.h_narrow, (size_t)m * rpitch * 2, cudaMemcpyHostToDevice, ctx->s_h2d));
+        CU_TRY(cudaEventRecord(s.ev_h2d, ctx->s_h2d));
+        CU_TRY(cudaStreamWaitEvent(ctx->stream, s.ev_h2d, 0));
+        CU_TRY(launch_widen(MMF_DT_U16, s.d_yraw, rpitch, s.d_y, pitch, m, pl.t_fit, ctx->sm_count, ctx->stream));
+        ++launches;
+        yk = s.d_y; ldk = pitch;
+        h2d += m * (int64_t)pl.t_fit * 2;
+      } else {
+        narrow = false;                                  // a value that uint16 cannot carry: float32 from here on
         if (it >= NBUF) CU_TRY(cudaStreamWaitEvent(ctx->s_h2d, s.ev_comp, 0));     // staging buffer free again
         if (ld_y == pitch)        // already pitched on the host: one contiguous copy (pad columns ride along, except
                                   // behind the caller's very last row, which may be the end of its buffer)

@@ -166,7 +166,8 @@ class ForecastEngine:
     """One library context: streams, staging buffers, the planned calendar design."""
 
     def __init__(self, device: int | None = None, kernel: str = "auto", assume_finite: bool = False,
-                 chunk_series: int = 0, stream: int | None = None, tc_variant: int = 0):
+                 chunk_series: int = 0, stream: int | None = None, tc_variant: int = 0,
+                 host_narrow: str = "auto", host_threads: int = 0):
         self._lib = N.load()
         cfg = N.MmfConfig()
         cfg.device = -1 if device is None else int(device)
@@ -175,6 +176,10 @@ class ForecastEngine:
         cfg.chunk_series = int(chunk_series)
         cfg.tc_variant = int(tc_variant)
         cfg.stream = stream
+        # host (NumPy) float32 input: narrow integer-valued chunks to uint16 on host threads so that half the bytes
+        # cross PCIe ("auto" / "on" / "off"); exact or not used -- the forecasts are bit-equal either way
+        cfg.host_narrow = {"auto": 0, "on": 1, "off": 2}[host_narrow]
+        cfg.host_threads = int(host_threads)
         h = C.c_void_p()
         N.check(self._lib.mmf_create(C.byref(cfg), C.byref(h)))
         self._h = h

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MMF_VERSION 101          /* 0.1.1 */
+#define MMF_VERSION 102          /* 0.1.2 */
 #define MMF_P 16                 /* design columns (zero-pad narrower designs) */
 #define MMF_PIVOT_TOL 1e-3f      /* per-series relative Cholesky pivot threshold */
 #define MMF_CAL_TOL 1e-10        /* aliasing threshold on the float64 calendar Gram */
@@ -72,6 +72,10 @@ typedef struct mmf_config {
                               experimental <8-stage, 2 staging tiles> one (same results) */
   int64_t chunk_series;    /* host-buffer path: series per pipelined chunk (0 = library default) */
   void*   stream;          /* cudaStream_t to enqueue on (NULL = library-owned stream) */
+  int32_t host_narrow;     /* host-buffer path: 0 = automatic, 1 = always try, 2 = never: narrow float32 chunks to
+                              uint16 on host threads when every value is an integer in [0, 65534] (exactly, or the
+                              chunk goes as float32), so that half the bytes cross PCIe; widened back on the device */
+  int32_t host_threads;    /* threads of that narrowing pool (0 = half of the process's cores, at most 24) */
 } mmf_config;
 
 typedef struct mmf_stats {

@@ -36,7 +36,8 @@ def test_constants_agree_between_header_python_and_oracle():
 
 
 def test_struct_layouts_match_header():
-    assert ctypes.sizeof(N.MmfConfig) == 32
+    assert ctypes.sizeof(N.MmfConfig) == 40          # device, kernel, assume_finite, tc_variant, chunk_series, stream,
+                                                     # host_narrow, host_threads (include/mmf.h)
     assert ctypes.sizeof(N.MmfStats) == 48
 
 
@@ -53,7 +54,7 @@ def test_product_package_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "dss-ml-at-scale_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 with open(os.path.join(dirpath, f)) as fh:
                     src = fh.read()
                 assert "import oracle" not in src and "from oracle" not in src, f

@@ -100,7 +100,8 @@ def test_config5_10m_by_365_device_and_host_spill():
     eng2 = mmf.ForecastEngine(chunk_series=262_144)
     eng2.plan_calendar(start, t, "D", h, "future")
     res = eng2.fit_forecast(yh, ps, npred, out=oh, want_status=True, want_stats=True)
-    assert res["stats"].h2d_bytes == n * t * 4 and res["stats"].d2h_bytes >= n * h * 4
+    # integer-valued demand: the host path narrows each chunk to uint16 on the way (exactly), half the bytes cross PCIe
+    assert res["stats"].h2d_bytes == n * t * 2 and res["stats"].d2h_bytes >= n * h * 4
     assert int((res["status"] != 0).sum()) == 0
     got = torch.from_numpy(oh)
     ref = dev["pred"].cpu()
@@ -432,3 +433,47 @@ def test_forecast_groups_many_calendars_future_mode_uses_one_ragged_launch():
     # weekly histories of 40-90 points extrapolated 8 weeks: leverage of a few units; scale the tolerance like the
     # packed tests do (forecast_leverage) with a bound that holds for every calendar of this batch
     _le(err.max(), 40 * tolerance(df["Demand"].to_numpy()), "ragged DataFrame batch vs per-group oracle UDF")
+
+
+# ---- host-side narrowing of float32 chunks (half the PCIe bytes), exact or not used ------------------------------------
+def test_host_narrowing_is_exact_or_not_used():
+    """mmf_fit_forecast_f32 with HOST float32 buffers: chunks whose finite values are all integers in [0, 65534] cross
+    PCIe as uint16 (narrowed on host threads, widened on the device); any other chunk goes as float32.  Either way the
+    forecasts equal the device-resident float32 path bit for bit."""
+    import torch
+    n, t, h = 6000, 365, 28
+    y, start = mmf.synth.daily_store_item_demand(n, t, seed=12, nan_frac=0.002)
+    y[100, :] = np.nan
+    y[101, 5] = np.inf
+    dev = mmf.ForecastEngine()
+    _, ps, npred = dev.plan_calendar(start, t, "D", h, "future")
+
+    def device_result(arr):
+        r = dev.fit_forecast(mmf.device_packed(arr), ps, npred, want_status=True)
+        torch.cuda.synchronize()
+        return r["pred"].cpu().numpy(), r["status"].cpu().numpy()
+
+    for mode, chunk in (("on", 700), ("on", 6000), ("off", 700)):
+        eng = mmf.ForecastEngine(chunk_series=chunk, host_narrow=mode, host_threads=4)
+        eng.plan_calendar(start, t, "D", h, "future")
+        yp = mmf.alloc_packed(n, t)
+        yp[...] = y
+        res = eng.fit_forecast(yp, ps, npred, want_status=True, want_stats=True)
+        wp, ws = device_result(y)
+        assert np.array_equal(res["pred"], wp, equal_nan=True) and np.array_equal(res["status"], ws), (mode, chunk)
+        assert res["stats"].h2d_bytes == n * t * (2 if mode == "on" else 4), (mode, chunk)
+        # pageable, unpitched rows narrow too
+        res2 = eng.fit_forecast(np.ascontiguousarray(y), ps, npred)
+        assert np.array_equal(res2, wp, equal_nan=True)
+        # a chunk with a value uint16 cannot carry exactly falls back to float32 from that chunk on
+        for badval in (0.5, -3.0, 70000.0):
+            y2 = y.copy()
+            y2[2000, 17] = badval
+            yp[...] = y2
+            r3 = eng.fit_forecast(yp, ps, npred, want_stats=True)
+            wp3, _ = device_result(y2)
+            assert np.array_equal(r3["pred"], wp3, equal_nan=True), (mode, chunk, badval)
+            if mode == "on" and chunk == 700:
+                assert n * t * 2 < r3["stats"].h2d_bytes < n * t * 4          # chunks 0-1 narrow, the rest float32
+        eng.close()
+    dev.close()
