@@ -683,6 +683,7 @@ static int fit_forecast_impl(mmf_ctx* ctx, const void* y_any, int32_t dtype, int
     const int64_t pitch = (pl.t_fit + 3) & ~3;                 // staged row pitch (floats), TMA-friendly
     const int64_t rpitch = (pl.t_fit + 7) & ~7;                // staged row pitch of an integer chunk (16-B rows)
     const int64_t opitch = (n_pred + 3) & ~3;
+    const int64_t npitch = (pl.t_fit + 15) & ~15;              // ... of a narrowed uint16 chunk (32-B rows: streaming stores)
     // float32 host input is narrowed to uint16 chunk by chunk on host threads while the previous chunk's copy is in
     // flight (exact or not used: host_narrow.cpp), so half the bytes cross PCIe -- the link is what bounds this path
     bool narrow = !is_int && !y_dev && ctx->cfg.host_narrow != 2 &&
@@ -692,7 +693,11 @@ static int fit_forecast_impl(mmf_ctx* ctx, const void* y_any, int32_t dtype, int
       if (want <= 0) {
         cpu_set_t set;
         const int have = (sched_getaffinity(0, sizeof(set), &set) == 0) ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
-        want = std::max(1, std::min(24, have / 2));
+        // measured on the 2 x 32-core host of the B200 box (64 logical CPUs local to the GPU): 8 / 16 / 24 / 32 / 48
+        // threads -> 78.8 / 55.7 / 65.2 / 84.7 / 124.6 ms per 1 M x 1,095 step (79 ms without narrowing): past ~16
+        // streaming threads the copy engine's reads of the same memory controllers slow down more than the
+        // conversion speeds up (profiles/r02/README.md)
+        want = std::max(1, std::min(16, have / 2));
       }
       ctx->narrow_pool = narrow_pool_create(want - 1);         // the calling thread is the last worker
     }
@@ -703,12 +708,12 @@ static int fit_forecast_impl(mmf_ctx* ctx, const void* y_any, int32_t dtype, int
       int rc = MMF_OK;
       if (!y_dev || is_int) rc = grow((void**)&s.d_y, &s.y_cap, (size_t)chunk * pitch * sizeof(float));
       if (rc == MMF_OK && (is_int || narrow) && !y_dev)
-        rc = grow(&s.d_yraw, &s.yraw_cap, (size_t)chunk * rpitch * (narrow ? 2 : esize));
-      if (rc == MMF_OK && narrow && s.h_narrow_cap < (size_t)chunk * rpitch * 2) {
+        rc = grow(&s.d_yraw, &s.yraw_cap, narrow ? (size_t)chunk * npitch * 2 : (size_t)chunk * rpitch * esize);
+      if (rc == MMF_OK && narrow && s.h_narrow_cap < (size_t)chunk * npitch * 2) {
         if (s.h_narrow) cudaFreeHost(s.h_narrow);
         s.h_narrow = nullptr; s.h_narrow_cap = 0;
-        if (cudaHostAlloc((void**)&s.h_narrow, (size_t)chunk * rpitch * 2, cudaHostAllocDefault) == cudaSuccess)
-          s.h_narrow_cap = (size_t)chunk * rpitch * 2;
+        if (cudaHostAlloc((void**)&s.h_narrow, (size_t)chunk * npitch * 2, cudaHostAllocDefault) == cudaSuccess)
+          s.h_narrow_cap = (size_t)chunk * npitch * 2;
         else { cudaGetLastError(); narrow = false; }           // cannot pin the slot: plain float32 copies
       }
       if (rc == MMF_OK && !o_dev) rc = grow((void**)&s.d_out, &s.out_cap, (size_t)chunk * opitch * sizeof(float));
@@ -750,13 +755,13 @@ static int fit_forecast_impl(mmf_ctx* ctx, const void* y_any, int32_t dtype, int
       else if (narrow && [&]() -> bool {
                  // the slot's previous copy (chunk it - NBUF) must have left the host buffer before it is rewritten
                  if (it >= NBUF && cudaEventSynchronize(s.ev_h2d) != cudaSuccess) return false;
-                 return narrow_f32_to_u16(ctx->narrow_pool, y + off * ld_y, ld_y, s.h_narrow, rpitch, m, pl.t_fit);
+                 return narrow_f32_to_u16(ctx->narrow_pool, y + off * ld_y, ld_y, s.h_narrow, npitch, m, pl.t_fit);
                }()) {
         if (it >= NBUF) CU_TRY(cudaStreamWaitEvent(ctx->s_h2d, s.ev_comp, 0));     // device staging free again
-        CU_TRY(cudaMemcpyAsync(s.d_yraw, s.h_narrow, (size_t)m * rpitch * 2, cudaMemcpyHostToDevice, ctx->s_h2d));
+        CU_TRY(cudaMemcpyAsync(s.d_yraw, s.h_narrow, (size_t)m * npitch * 2, cudaMemcpyHostToDevice, ctx->s_h2d));
         CU_TRY(cudaEventRecord(s.ev_h2d, ctx->s_h2d));
         CU_TRY(cudaStreamWaitEvent(ctx->stream, s.ev_h2d, 0));
-        CU_TRY(launch_widen(MMF_DT_U16, s.d_yraw, rpitch, s.d_y, pitch, m, pl.t_fit, ctx->sm_count, ctx->stream));
+        CU_TRY(launch_widen(MMF_DT_U16, s.d_yraw, npitch, s.d_y, pitch, m, pl.t_fit, ctx->sm_count, ctx->stream));
         ++launches;
         yk = s.d_y; ldk = pitch;
         h2d += m * (int64_t)pl.t_fit * 2;

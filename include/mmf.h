@@ -75,7 +75,7 @@ typedef struct mmf_config {
   int32_t host_narrow;     /* host-buffer path: 0 = automatic, 1 = always try, 2 = never: narrow float32 chunks to
                               uint16 on host threads when every value is an integer in [0, 65534] (exactly, or the
                               chunk goes as float32), so that half the bytes cross PCIe; widened back on the device */
-  int32_t host_threads;    /* threads of that narrowing pool (0 = half of the process's cores, at most 24) */
+  int32_t host_threads;    /* threads of that narrowing pool (0 = half of the process's cores, at most 16) */
 } mmf_config;
 
 typedef struct mmf_stats {
