@@ -23,7 +23,8 @@ namespace mmf {
 namespace {
 
 // rows [r0, r1): returns false as soon as a value cannot be carried exactly
-bool narrow_rows(const float* src, int64_t ld_src, uint16_t* dst, int64_t ld_dst, int64_t r0, int64_t r1, int32_t t) {
+bool narrow_rows(const float* src, int64_t ld_src, uint16_t* dst, int64_t ld_dst, int64_t r0, int64_t r1, int32_t t,
+                 bool stream_stores) {
   for (int64_t r = r0; r < r1; ++r) {
     const float* s = src + r * ld_src;
     uint16_t* d = dst + r * ld_dst;
@@ -33,11 +34,14 @@ bool narrow_rows(const float* src, int64_t ld_src, uint16_t* dst, int64_t ld_dst
     const __m256i maxv = _mm256_set1_epi32(65534);
     const __m256i miss = _mm256_set1_epi32(65535);
     __m256i bad = _mm256_setzero_si256();
-    // the destination slot is page-locked memory the DMA engine reads next: streaming (non-temporal) stores keep the
-    // read-for-ownership traffic off a memory system this path already loads with 6.6 B per value
-    const bool nt = (reinterpret_cast<uintptr_t>(d) & 31u) == 0;
+    // Two regimes for the destination (a page-locked slot the copy engine reads next):
+    //  * small slots that stay in the last-level cache: ordinary stores -- the copy engine's reads are then served
+    //    from the cache and the only DRAM traffic of the whole pass is the 4 B per value read from the caller's buffer;
+    //  * slots larger than the cache: streaming stores, no read-for-ownership traffic.
+    // The source is read once: non-temporal prefetch keeps it from pushing the slots out of the cache.
+    const bool nt = stream_stores && (reinterpret_cast<uintptr_t>(d) & 31u) == 0;
     for (; k + 16 <= t; k += 16) {
-      _mm_prefetch(reinterpret_cast<const char*>(s + k + 256), _MM_HINT_T0);      // 1 KB ahead in the row stream
+      _mm_prefetch(reinterpret_cast<const char*>(s + k + 256), _MM_HINT_NTA);     // 1 KB ahead in the row stream
       const __m256 v0 = _mm256_loadu_ps(s + k), v1 = _mm256_loadu_ps(s + k + 8);
       const __m256i b0 = _mm256_castps_si256(v0), b1 = _mm256_castps_si256(v1);
       const __m256i nf0 = _mm256_cmpeq_epi32(_mm256_and_si256(b0, expm), expm);      // NaN / Inf
@@ -103,8 +107,8 @@ class NarrowPool {
   ~NarrowPool() {
     {
       std::lock_guard<std::mutex> lk(mu_);
-      stop_ = true;
-      ++gen_;
+      stop_.store(true);
+      gen_.fetch_add(1, std::memory_order_release);
     }
     cv_.notify_all();
     for (auto& w : workers_) w.join();
@@ -112,26 +116,30 @@ class NarrowPool {
   int size() const { return (int)workers_.size(); }
 
   // float32 rows -> uint16 rows; false (and dst unspecified) when some value is not exactly representable
-  bool run(const float* src, int64_t ld_src, uint16_t* dst, int64_t ld_dst, int64_t n, int32_t t) {
-    job_ = Job{src, ld_src, dst, ld_dst, n, t};
+  // between begin_call() and end_call() the workers spin on the generation counter instead of sleeping on the
+  // condition variable: a call narrows hundreds of small sub-chunks back to back and a futex wake per sub-chunk
+  // and worker would cost more than the narrowing itself
+  void begin_call() { hot_.store(true, std::memory_order_release); { std::lock_guard<std::mutex> lk(mu_); } cv_.notify_all(); }
+  void end_call() { hot_.store(false, std::memory_order_release); }
+
+  bool run(const float* src, int64_t ld_src, uint16_t* dst, int64_t ld_dst, int64_t n, int32_t t, bool stream_stores) {
+    job_ = Job{src, ld_src, dst, ld_dst, n, t, stream_stores};
     next_.store(0, std::memory_order_relaxed);
     ok_.store(true, std::memory_order_relaxed);
+    pending_.store((int)workers_.size(), std::memory_order_relaxed);
     {
       std::lock_guard<std::mutex> lk(mu_);
-      pending_ = (int)workers_.size();
-      ++gen_;
+      gen_.fetch_add(1, std::memory_order_release);
     }
-    cv_.notify_all();
+    if (!hot_.load(std::memory_order_relaxed)) cv_.notify_all();
     work();                                        // the calling thread helps
-    _mm_sfence();
-    std::unique_lock<std::mutex> lk(mu_);
-    done_.wait(lk, [this] { return pending_ == 0; });
+    while (pending_.load(std::memory_order_acquire) != 0) _mm_pause();
     return ok_.load(std::memory_order_relaxed);
   }
 
  private:
-  struct Job { const float* src; int64_t ld_src; uint16_t* dst; int64_t ld_dst; int64_t n; int32_t t; };
-  static constexpr int64_t BLOCK = 256;            // rows per grab: ~1 MB of float32 at T = 1,095
+  struct Job { const float* src; int64_t ld_src; uint16_t* dst; int64_t ld_dst; int64_t n; int32_t t; bool stream_stores; };
+  static constexpr int64_t BLOCK = 64;             // rows per grab: ~280 KB of float32 at T = 1,095
 
   void work() {
     const Job j = job_;
@@ -139,33 +147,35 @@ class NarrowPool {
       const int64_t r0 = next_.fetch_add(BLOCK, std::memory_order_relaxed);
       if (r0 >= j.n || !ok_.load(std::memory_order_relaxed)) break;
       const int64_t r1 = r0 + BLOCK < j.n ? r0 + BLOCK : j.n;
-      if (!narrow_rows(j.src, j.ld_src, j.dst, j.ld_dst, r0, r1, j.t)) ok_.store(false, std::memory_order_relaxed);
+      if (!narrow_rows(j.src, j.ld_src, j.dst, j.ld_dst, r0, r1, j.t, j.stream_stores)) ok_.store(false, std::memory_order_relaxed);
     }
     _mm_sfence();                                  // streaming stores are globally visible before the copy is enqueued
   }
   void loop() {
     uint64_t seen = 0;
     for (;;) {
-      {
+      // hot: spin (a call is in progress, the next sub-chunk is microseconds away); cold: sleep
+      int spins = 0;
+      while (gen_.load(std::memory_order_acquire) == seen) {
+        if (hot_.load(std::memory_order_relaxed) && spins < (1 << 20)) { _mm_pause(); ++spins; continue; }
         std::unique_lock<std::mutex> lk(mu_);
-        cv_.wait(lk, [&] { return gen_ != seen; });
-        seen = gen_;
-        if (stop_) return;
+        cv_.wait(lk, [&] { return gen_.load(std::memory_order_acquire) != seen || hot_.load(std::memory_order_relaxed); });
+        spins = 0;
       }
+      seen = gen_.load(std::memory_order_acquire);
+      if (stop_) return;
       work();
-      {
-        std::lock_guard<std::mutex> lk(mu_);
-        if (--pending_ == 0) done_.notify_one();
-      }
+      pending_.fetch_sub(1, std::memory_order_release);
     }
   }
 
   std::vector<std::thread> workers_;
   std::mutex mu_;
-  std::condition_variable cv_, done_;
-  bool stop_;
-  uint64_t gen_;
-  int pending_;
+  std::condition_variable cv_;
+  std::atomic<bool> stop_;
+  std::atomic<uint64_t> gen_;
+  std::atomic<int> pending_;
+  std::atomic<bool> hot_{false};
   Job job_{};
   std::atomic<int64_t> next_{0};
   std::atomic<bool> ok_{true};
@@ -174,8 +184,11 @@ class NarrowPool {
 NarrowPool* narrow_pool_create(int n_threads) { return new NarrowPool(n_threads > 0 ? n_threads : 1); }
 void narrow_pool_destroy(NarrowPool* p) { delete p; }
 int narrow_pool_size(const NarrowPool* p) { return p ? p->size() + 1 : 0; }
-bool narrow_f32_to_u16(NarrowPool* p, const float* src, int64_t ld_src, uint16_t* dst, int64_t ld_dst, int64_t n, int32_t t) {
-  return p->run(src, ld_src, dst, ld_dst, n, t);
+bool narrow_f32_to_u16(NarrowPool* p, const float* src, int64_t ld_src, uint16_t* dst, int64_t ld_dst, int64_t n, int32_t t,
+                       bool stream_stores) {
+  return p->run(src, ld_src, dst, ld_dst, n, t, stream_stores);
 }
+void narrow_pool_begin_call(NarrowPool* p) { p->begin_call(); }
+void narrow_pool_end_call(NarrowPool* p) { p->end_call(); }
 
 }  // namespace mmf

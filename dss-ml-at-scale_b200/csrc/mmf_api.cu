@@ -25,7 +25,10 @@ class NarrowPool;
 NarrowPool* narrow_pool_create(int n_threads);
 void narrow_pool_destroy(NarrowPool* p);
 int narrow_pool_size(const NarrowPool* p);
-bool narrow_f32_to_u16(NarrowPool* p, const float* src, int64_t ld_src, uint16_t* dst, int64_t ld_dst, int64_t n, int32_t t);
+bool narrow_f32_to_u16(NarrowPool* p, const float* src, int64_t ld_src, uint16_t* dst, int64_t ld_dst, int64_t n, int32_t t,
+                       bool stream_stores);
+void narrow_pool_begin_call(NarrowPool* p);
+void narrow_pool_end_call(NarrowPool* p);
 }  // namespace mmf
 
 namespace {
@@ -125,7 +128,14 @@ struct Staging {
   float* d_beta = nullptr;   size_t beta_cap = 0;
   int32_t* d_status = nullptr; size_t status_cap = 0;
   cudaEvent_t ev_h2d = nullptr, ev_comp = nullptr, ev_d2h = nullptr;
-  uint16_t* h_narrow = nullptr; size_t h_narrow_cap = 0;   // pinned HOST slot: the chunk narrowed to uint16 (host_narrow.cpp)
+};
+
+// Page-locked HOST slots the narrowed (uint16) sub-chunks are written to and copied from (host_narrow.cpp): the
+// narrowing of sub-chunk k+1 runs while the copy of sub-chunk k is in flight.
+constexpr int NHOST = 4;
+struct HostSlot {
+  uint16_t* p = nullptr; size_t cap = 0;
+  cudaEvent_t ev = nullptr;              // the copy out of the slot has completed
 };
 
 }  // namespace
@@ -162,6 +172,8 @@ struct mmf_ctx {
   MultiPlan multi;
   Staging st[NBUF];
   NarrowPool* narrow_pool = nullptr;   // created on the first host-buffer call that narrows
+  HostSlot hslot[NHOST];
+  uint64_t hslot_uses = 0;
 };
 
 namespace {
@@ -497,12 +509,16 @@ int mmf_destroy(mmf_ctx* ctx) {
   for (int i = 0; i < NBUF; ++i) {
     Staging& s = ctx->st[i];
     cudaFree(s.d_y); cudaFree(s.d_yraw); cudaFree(s.d_out); cudaFree(s.d_beta); cudaFree(s.d_status);
-    if (s.h_narrow) cudaFreeHost(s.h_narrow);
+
     if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
     if (s.ev_comp) cudaEventDestroy(s.ev_comp);
     if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
   }
   if (ctx->narrow_pool) narrow_pool_destroy(ctx->narrow_pool);
+  for (int i = 0; i < NHOST; ++i) {
+    if (ctx->hslot[i].p) cudaFreeHost(ctx->hslot[i].p);
+    if (ctx->hslot[i].ev) cudaEventDestroy(ctx->hslot[i].ev);
+  }
   cudaFree(ctx->d_pending);
   cudaFree(ctx->d_recs);
   cudaFree(ctx->d_rec_rows);
@@ -686,8 +702,15 @@ static int fit_forecast_impl(mmf_ctx* ctx, const void* y_any, int32_t dtype, int
     const int64_t npitch = (pl.t_fit + 15) & ~15;              // ... of a narrowed uint16 chunk (32-B rows: streaming stores)
     // float32 host input is narrowed to uint16 chunk by chunk on host threads while the previous chunk's copy is in
     // flight (exact or not used: host_narrow.cpp), so half the bytes cross PCIe -- the link is what bounds this path
-    bool narrow = !is_int && !y_dev && ctx->cfg.host_narrow != 2 &&
-                  (ctx->cfg.host_narrow == 1 || n * (int64_t)pl.t_fit >= ((int64_t)4 << 20));
+    // Automatic mode narrows only where it was measured to pay: batches of at least 4 M values, and a host with at least
+    // 64 logical CPUs per visible GPU -- the narrowing pool and the copy engine share the host's memory controllers, and
+    // with one process per GPU on an 8-GPU host the plain float32 copies are already bound by host memory, not by PCIe.
+    bool narrow = !is_int && !y_dev && ctx->cfg.host_narrow != 2;
+    if (narrow && ctx->cfg.host_narrow != 1) {
+      int ndev = 1;
+      if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); ndev = 1; }
+      narrow = n * (int64_t)pl.t_fit >= ((int64_t)4 << 20) && (int)std::thread::hardware_concurrency() / ndev >= 64;
+    }
     if (narrow && ctx->narrow_pool == nullptr) {
       int want = ctx->cfg.host_threads;
       if (want <= 0) {
@@ -701,6 +724,32 @@ static int fit_forecast_impl(mmf_ctx* ctx, const void* y_any, int32_t dtype, int
       }
       ctx->narrow_pool = narrow_pool_create(want - 1);         // the calling thread is the last worker
     }
+    // rows per narrowed sub-chunk and store flavour: measured on the B200 box (16 threads, 1 M x 1,095 per step; float32
+    // copies: 82.4 ms): 1,024 / 2,048 / 4,096 / 8,192 / 32,768 rows with ordinary stores 84.6 / 81.6 / 75.1 / 62.2 /
+    // 63.9 ms, streaming stores 67.1 ms at 4,096 and 63.6 ms at 32,768 -- keeping the slots cache resident (small
+    // sub-chunks, ordinary stores) does not pay for the extra copies and synchronisations; 8,192 rows it is
+    int64_t sub_rows = 8192;
+    bool stream_stores = true;
+    if (const char* e = getenv("MMF_HOST_SUB_ROWS")) sub_rows = std::max<int64_t>(64, atoll(e));   // tuning / experiments
+    if (const char* e = getenv("MMF_HOST_STREAM_STORES")) stream_stores = atoi(e) != 0;
+    sub_rows = std::min(sub_rows, chunk);
+    if (narrow) {
+      for (int i = 0; i < NHOST && narrow; ++i) {
+        HostSlot& hs = ctx->hslot[i];
+        if (!hs.ev && cudaEventCreateWithFlags(&hs.ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); narrow = false; break; }
+        const size_t need = (size_t)sub_rows * npitch * 2;
+        if (hs.cap >= need) continue;
+        if (hs.p) { cudaEventSynchronize(hs.ev); cudaFreeHost(hs.p); }
+        hs.p = nullptr; hs.cap = 0;
+        if (cudaHostAlloc((void**)&hs.p, need, cudaHostAllocDefault) == cudaSuccess) hs.cap = need;
+        else { cudaGetLastError(); narrow = false; }           // cannot pin the slots: plain float32 copies
+      }
+    }
+    struct HotScope {                                           // workers spin between sub-chunks only during this call
+      NarrowPool* p;
+      explicit HotScope(NarrowPool* q) : p(q) { if (p) narrow_pool_begin_call(p); }
+      ~HotScope() { if (p) narrow_pool_end_call(p); }
+    } hot_scope(narrow ? ctx->narrow_pool : nullptr);
     const mmf_ctx* pinned_scope = g_grow_ctx;
     g_grow_ctx = nullptr;                                       // staging slots are never part of a captured graph
     for (int i = 0; i < NBUF; ++i) {
@@ -709,13 +758,6 @@ static int fit_forecast_impl(mmf_ctx* ctx, const void* y_any, int32_t dtype, int
       if (!y_dev || is_int) rc = grow((void**)&s.d_y, &s.y_cap, (size_t)chunk * pitch * sizeof(float));
       if (rc == MMF_OK && (is_int || narrow) && !y_dev)
         rc = grow(&s.d_yraw, &s.yraw_cap, narrow ? (size_t)chunk * npitch * 2 : (size_t)chunk * rpitch * esize);
-      if (rc == MMF_OK && narrow && s.h_narrow_cap < (size_t)chunk * npitch * 2) {
-        if (s.h_narrow) cudaFreeHost(s.h_narrow);
-        s.h_narrow = nullptr; s.h_narrow_cap = 0;
-        if (cudaHostAlloc((void**)&s.h_narrow, (size_t)chunk * npitch * 2, cudaHostAllocDefault) == cudaSuccess)
-          s.h_narrow_cap = (size_t)chunk * npitch * 2;
-        else { cudaGetLastError(); narrow = false; }           // cannot pin the slot: plain float32 copies
-      }
       if (rc == MMF_OK && !o_dev) rc = grow((void**)&s.d_out, &s.out_cap, (size_t)chunk * opitch * sizeof(float));
       if (rc == MMF_OK && out_beta && !b_dev) rc = grow((void**)&s.d_beta, &s.beta_cap, (size_t)chunk * P * sizeof(float));
       if (rc == MMF_OK && (!out_status || !s_dev)) rc = grow((void**)&s.d_status, &s.status_cap, (size_t)chunk * sizeof(int32_t));
@@ -753,12 +795,22 @@ static int fit_forecast_impl(mmf_ctx* ctx, const void* y_any, int32_t dtype, int
         yk = s.d_y; ldk = pitch;
       } else if (y_dev) { yk = y + off * ld_y; ldk = ld_y; }
       else if (narrow && [&]() -> bool {
-                 // the slot's previous copy (chunk it - NBUF) must have left the host buffer before it is rewritten
-                 if (it >= NBUF && cudaEventSynchronize(s.ev_h2d) != cudaSuccess) return false;
-                 return narrow_f32_to_u16(ctx->narrow_pool, y + off * ld_y, ld_y, s.h_narrow, npitch, m, pl.t_fit);
+                 // sub-chunk by sub-chunk: narrow into a (cache-resident) host slot, copy it into the chunk's device
+                 // staging; the narrowing of sub-chunk k+1 runs while the copy of sub-chunk k is in flight
+                 if (it >= NBUF && cudaStreamWaitEvent(ctx->s_h2d, s.ev_comp, 0) != cudaSuccess) return false;   // device staging free
+                 for (int64_t so = 0; so < m; so += sub_rows) {
+                   const int64_t ms = std::min(sub_rows, m - so);
+                   HostSlot& hs = ctx->hslot[ctx->hslot_uses % NHOST];
+                   if (ctx->hslot_uses >= (uint64_t)NHOST && cudaEventSynchronize(hs.ev) != cudaSuccess) return false;
+                   if (!narrow_f32_to_u16(ctx->narrow_pool, y + (off + so) * ld_y, ld_y, hs.p, npitch, ms, pl.t_fit, stream_stores))
+                     return false;                           // not representable: the whole chunk goes as float32
+                   if (cudaMemcpyAsync(static_cast<uint16_t*>(s.d_yraw) + so * npitch, hs.p, (size_t)ms * npitch * 2,
+                                       cudaMemcpyHostToDevice, ctx->s_h2d) != cudaSuccess) return false;
+                   if (cudaEventRecord(hs.ev, ctx->s_h2d) != cudaSuccess) return false;
+                   ++ctx->hslot_uses;
+                 }
+                 return true;
                }()) {
-        if (it >= NBUF) CU_TRY(cudaStreamWaitEvent(ctx->s_h2d, s.ev_comp, 0));     // device staging free again
-        CU_TRY(cudaMemcpyAsync(s.d_yraw, s.h_narrow, (size_t)m * npitch * 2, cudaMemcpyHostToDevice, ctx->s_h2d));
         CU_TRY(cudaEventRecord(s.ev_h2d, ctx->s_h2d));
         CU_TRY(cudaStreamWaitEvent(ctx->stream, s.ev_h2d, 0));
         CU_TRY(launch_widen(MMF_DT_U16, s.d_yraw, npitch, s.d_y, pitch, m, pl.t_fit, ctx->sm_count, ctx->stream));
