@@ -7,8 +7,6 @@
 // same float32 staging rows the kernels read.  The narrowing is exact or it is not used: a chunk in which any finite
 // value is not an integer in [0, 65534] is sent as float32 like before.  NaN / Inf (missing) -> 65535.
 #include <immintrin.h>
-#include <pthread.h>
-#include <sched.h>
 #include <stdint.h>
 
 #include <atomic>
@@ -83,26 +81,9 @@ bool narrow_rows(const float* src, int64_t ld_src, uint16_t* dst, int64_t ld_dst
 class NarrowPool {
  public:
   explicit NarrowPool(int n_threads) : stop_(false), gen_(0), pending_(0) {
-    // one worker per core of the process's affinity mask, in mask order: on the usual enumeration (physical cores first,
-    // their SMT siblings after) that spreads up to half the mask over distinct physical cores; two workers landing on
-    // one core's siblings was measured slower than half as many workers
-    cpu_set_t set;
-    std::vector<int> cpus;
-    if (sched_getaffinity(0, sizeof(set), &set) == 0)
-      for (int c = 0; c < CPU_SETSIZE; ++c)
-        if (CPU_ISSET(c, &set)) cpus.push_back(c);
-    for (int i = 0; i < n_threads; ++i) {
-      const int cpu = (int)cpus.size() > i + 1 ? cpus[i + 1] : -1;       // cpus[0] is left to the calling thread
-      workers_.emplace_back([this, cpu] {
-        if (cpu >= 0) {
-          cpu_set_t one;
-          CPU_ZERO(&one);
-          CPU_SET(cpu, &one);
-          pthread_setaffinity_np(pthread_self(), sizeof(one), &one);
-        }
-        loop();
-      });
-    }
+    // workers are NOT pinned: several processes (one per GPU) may share a NUMA node's cores, and the scheduler spreads
+    // 16 runnable threads over idle cores by itself
+    for (int i = 0; i < n_threads; ++i) workers_.emplace_back([this] { loop(); });
   }
   ~NarrowPool() {
     {

@@ -702,14 +702,15 @@ static int fit_forecast_impl(mmf_ctx* ctx, const void* y_any, int32_t dtype, int
     const int64_t npitch = (pl.t_fit + 15) & ~15;              // ... of a narrowed uint16 chunk (32-B rows: streaming stores)
     // float32 host input is narrowed to uint16 chunk by chunk on host threads while the previous chunk's copy is in
     // flight (exact or not used: host_narrow.cpp), so half the bytes cross PCIe -- the link is what bounds this path
-    // Automatic mode narrows only where it was measured to pay: batches of at least 4 M values, and a host with at least
-    // 64 logical CPUs per visible GPU -- the narrowing pool and the copy engine share the host's memory controllers, and
-    // with one process per GPU on an 8-GPU host the plain float32 copies are already bound by host memory, not by PCIe.
+    // Automatic mode narrows only where it was measured to pay: batches of at least 4 M values on a host where this
+    // process sees ONE GPU and at least 32 CPUs.  The narrowing pool and the copy engine share the host's memory
+    // controllers; with one process per GPU on a multi-GPU host the plain float32 copies are already bound by host
+    // memory rather than by PCIe, and several pools would fight over the same cores (host_narrow = 1 opts in anyway).
     bool narrow = !is_int && !y_dev && ctx->cfg.host_narrow != 2;
     if (narrow && ctx->cfg.host_narrow != 1) {
       int ndev = 1;
       if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); ndev = 1; }
-      narrow = n * (int64_t)pl.t_fit >= ((int64_t)4 << 20) && (int)std::thread::hardware_concurrency() / ndev >= 64;
+      narrow = n * (int64_t)pl.t_fit >= ((int64_t)4 << 20) && ndev == 1 && std::thread::hardware_concurrency() >= 32;
     }
     if (narrow && ctx->narrow_pool == nullptr) {
       int want = ctx->cfg.host_threads;
