@@ -42,6 +42,8 @@ class MmfConfig(C.Structure):
         ("stream", C.c_void_p),
         ("host_narrow", C.c_int32),
         ("host_threads", C.c_int32),
+        ("stream_solve", C.c_int32),
+        ("reserved1", C.c_int32),
     ]
 
 

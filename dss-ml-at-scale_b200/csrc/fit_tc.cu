@@ -95,8 +95,18 @@ __device__ __forceinline__ float centring_constant(const float* __restrict__ yro
 
 // MULTI: a ragged launch -- every 128-row tile names its calendar (mv.tiles / mv.cals); `n_chunks` is then only the
 // minimum over the calendars (>= 2).  MULTI == false compiles to the single-calendar kernel.
+// Register budget: ptxas takes 128 registers with __launch_bounds__(448, 1); capped at MMF_TC_MAXNREG (80: two small
+// spills in the epilogue) the CTA leaves room for one 128-thread block of the streaming solve on the same SM.
+#if !defined(MMF_TC_MAXNREG) && !defined(MMF_TC_NO_MAXNREG)
+#define MMF_TC_MAXNREG 80
+#endif
+#ifdef MMF_TC_MAXNREG
+#define MMF_TC_KERNEL_ATTR __maxnreg__(MMF_TC_MAXNREG)
+#else
+#define MMF_TC_KERNEL_ATTR __launch_bounds__(THREADS, 1)
+#endif
 template <int STAGES, int OBUF, bool MULTI>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void MMF_TC_KERNEL_ATTR
 fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const FitArgs a,
               uint32_t* __restrict__ pending_count, const int n_tiles, const int n_chunks, const MultiView mv) {
   using SmemLayout = SmemLayoutT<STAGES, OBUF>;
@@ -139,7 +149,10 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
   const int lane = threadIdx.x & 31;
 
   // ---- one-time setup
-  if (blockIdx.x == 0 && threadIdx.x == 0 && a.zero_next != nullptr) { a.zero_next[0] = 0u; a.zero_next[1] = 0u; }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.zero_next != nullptr) {
+#pragma unroll
+    for (int i = 0; i < CTR_WORDS; ++i) a.zero_next[i] = 0u;
+  }
   if (warp == WARP_MMA) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) {
@@ -178,6 +191,10 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // This CTA is resident: a dependent kernel launched behind this one with programmatic stream serialisation may start
+  // once EVERY CTA has said so -- the streaming solve then finds all producers running (it never has to wait for a
+  // producer that cannot get an SM), the early-exit fix-up kernels hide their launch latency under this kernel's tail.
+  if (threadIdx.x == 0) pdl_launch_dependents();
 
   if (warp == WARP_PROD) {
     // =========================== TMA producer ===========================
@@ -457,7 +474,16 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
           rec.nm[1] = static_cast<uint16_t>(nm1);
           rec.cal = tr.cal;
           const unsigned slot = base + __popc(dm & ((1u << lane) - 1u));
-          if (slot < a.rec_cap) a.rec_rows[slot] = row;
+          if (slot < a.rec_cap) {
+            if (a.stream_ctl != nullptr) {
+              // publish: the record (this thread's moments, the transform warps' positions acquired through bar_nm) is
+              // ordered before the work-list entry the consumer polls
+              __threadfence();
+              st_release_s64(a.rec_rows + slot, row);
+            } else {
+              a.rec_rows[slot] = row;
+            }
+          }
         }
       }
       if (bulk) {
@@ -526,6 +552,14 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
       }
     }
     if (bulk && warp == WARP_EPI0) bulk_wait_all_elect();   // global writes complete before the kernel retires
+    if (a.stream_ctl != nullptr) {
+      // the last CTA to finish tells the streaming solve that the work list is final
+      named_bar_sync(3, 128);
+      if (threadIdx.x == WARP_EPI0 * 32) {
+        __threadfence();
+        if (atomicAdd(a.stream_ctl + 1, 1u) == gridDim.x - 1u) st_release_u32(a.stream_ctl + 2, 1u);
+      }
+    }
   }
 
   // ---- teardown

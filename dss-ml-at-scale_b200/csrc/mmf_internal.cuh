@@ -102,6 +102,8 @@ struct FitArgs {
   int32_t only_pending;     // 1: process only rows whose status == MMF_STATUS_PENDING
   const uint32_t* pending_count;  // nullable; if non-null and *pending_count == 0 the kernel exits at once
   uint32_t* zero_next;      // nullable: 2 counters of the NEXT call's set, zeroed by the tcgen05 kernel (no memset node)
+  uint32_t* stream_ctl;     // nullable: {claimed, CTAs finished, producer done} of the streaming solve (solve_stream_kernel
+                            // consumes the queued records WHILE the tcgen05 kernel is still producing them)
   int64_t row_base;         // ragged fallback launches cover one calendar's rows: absolute row of this launch's row 0
   int32_t cal_id;           //   ... and that calendar's index (written into the records the launch queues)
 };
@@ -114,6 +116,11 @@ size_t fit_warp_smem_bytes(const DesignView& d, int* smem_rows);
 // pivot dropping and both triangular solves entirely in registers, then the forecasts
 cudaError_t launch_solve_rows(const DesignView& d, const FitArgs& a, int sm_count, cudaStream_t s,
                               const CalMeta* cals = nullptr);
+// the same solve as a CONSUMER that runs beside fit_tc_kernel (launched right behind it with programmatic stream
+// serialisation; fit_tc_kernel releases it once all its CTAs are resident): records are solved as the epilogue
+// publishes them, the kernel retires when the producer has finished and the work list is drained
+cudaError_t launch_solve_stream(const DesignView& d, const FitArgs& a, int sm_count, cudaStream_t s);
+constexpr int CTR_WORDS = 8;             // one counter set: {pending, records queued, claimed, CTAs finished, producer done, -, -, -}
 
 // fitted values + forecasts for MANY prediction rows (the reference's "Demand_Fitted for every date"
 // contract, 02:484-494): out[n, n_pred] = c + gamma A_pred^T as a tcgen05 GEMM with TMA-stored tiles

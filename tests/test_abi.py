@@ -36,8 +36,8 @@ def test_constants_agree_between_header_python_and_oracle():
 
 
 def test_struct_layouts_match_header():
-    assert ctypes.sizeof(N.MmfConfig) == 40          # device, kernel, assume_finite, tc_variant, chunk_series, stream,
-                                                     # host_narrow, host_threads (include/mmf.h)
+    assert ctypes.sizeof(N.MmfConfig) == 48          # device, kernel, assume_finite, tc_variant, chunk_series, stream,
+                                                     # host_narrow, host_threads, stream_solve, reserved1 (include/mmf.h)
     assert ctypes.sizeof(N.MmfStats) == 48
 
 
