@@ -95,11 +95,10 @@ __device__ __forceinline__ float centring_constant(const float* __restrict__ yro
 
 // MULTI: a ragged launch -- every 128-row tile names its calendar (mv.tiles / mv.cals); `n_chunks` is then only the
 // minimum over the calendars (>= 2).  MULTI == false compiles to the single-calendar kernel.
-// Register budget: ptxas takes 128 registers with __launch_bounds__(448, 1); capped at MMF_TC_MAXNREG (80: two small
-// spills in the epilogue) the CTA leaves room for one 128-thread block of the streaming solve on the same SM.
-#if !defined(MMF_TC_MAXNREG) && !defined(MMF_TC_NO_MAXNREG)
-#define MMF_TC_MAXNREG 80
-#endif
+// Register budget: ptxas takes 128 registers with __launch_bounds__(448, 1).  -DMMF_TC_MAXNREG=80 caps the kernel so that
+// one 128-thread block of the streaming solve (solve_stream_kernel, 214 registers) fits beside the CTA on an SM -- an
+// experiment that did not pay: at 80 registers the transform loop loses its load/compute overlap and the gap-free step
+// goes from 0.739 to 0.924 ms (2 % NaN: 1.985 ms instead of 1.449), DESIGN.md section 6b.
 #ifdef MMF_TC_MAXNREG
 #define MMF_TC_KERNEL_ATTR __maxnreg__(MMF_TC_MAXNREG)
 #else

@@ -339,10 +339,12 @@ int run_device_slab(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, int32
   if (capturing || !ctx->set_clean[cs]) CU_TRY(cudaMemsetAsync(counters, 0, CTR_WORDS * sizeof(uint32_t), s));
   if (!capturing) ctx->set_clean[cs] = false;             // dirty from here on, whatever happens below
   if (kernel == MMF_KERNEL_TC && !capturing) a.zero_next = ctx->d_pending + CTR_WORDS * (cs ^ 1);
-  // Streaming solve: the series with gaps are solved WHILE the tcgen05 kernel is still streaming (solve_stream_kernel
-  // beside fit_tc_kernel on every SM) instead of in a pass of their own afterwards.  The work list starts out as -1;
-  // the producer publishes row indices into it.
-  const bool stream_solve = kernel == MMF_KERNEL_TC && may_mask && !capturing && n >= 32768 && ctx->cfg.stream_solve != 2;
+  // Streaming solve (opt-in, mmf_config.stream_solve = 1): the series with gaps are solved WHILE the tcgen05 kernel is
+  // still streaming (solve_stream_kernel launched right behind it with programmatic stream serialisation) instead of in
+  // a pass of their own afterwards.  The work list starts out as -1; the producer publishes row indices into it.  It
+  // only overlaps when a consumer block fits beside the fit CTA on an SM, which needs the 80-register build of
+  // fit_tc_kernel -- and that build is slower than what the overlap wins, so it is off by default.
+  const bool stream_solve = kernel == MMF_KERNEL_TC && may_mask && !capturing && n >= 32768 && ctx->cfg.stream_solve == 1;
   if (stream_solve) {
     if (!ctx->rec_rows_clean) CU_TRY(cudaMemsetAsync(ctx->d_rec_rows, 0xFF, ctx->rec_rows_cap_bytes, s));
     ctx->rec_rows_clean = true;                            // the call's closing solve_rows pass resets what it consumed

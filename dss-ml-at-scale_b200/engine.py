@@ -167,7 +167,7 @@ class ForecastEngine:
 
     def __init__(self, device: int | None = None, kernel: str = "auto", assume_finite: bool = False,
                  chunk_series: int = 0, stream: int | None = None, tc_variant: int = 0,
-                 host_narrow: str = "auto", host_threads: int = 0, stream_solve: str = "auto"):
+                 host_narrow: str = "auto", host_threads: int = 0, stream_solve: bool = False):
         self._lib = N.load()
         cfg = N.MmfConfig()
         cfg.device = -1 if device is None else int(device)
@@ -180,8 +180,9 @@ class ForecastEngine:
         # cross PCIe ("auto" / "on" / "off"); exact or not used -- the forecasts are bit-equal either way
         cfg.host_narrow = {"auto": 0, "on": 1, "off": 2}[host_narrow]
         cfg.host_threads = int(host_threads)
-        # series with gaps: "auto" solves them beside the streaming kernel (solve_stream_kernel), "off" in a pass after it
-        cfg.stream_solve = {"auto": 0, "off": 2}[stream_solve]
+        # series with gaps: True = solve them beside the streaming kernel (solve_stream_kernel; experimental), False = in
+        # a pass of their own after it
+        cfg.stream_solve = 1 if stream_solve else 0
         h = C.c_void_p()
         N.check(self._lib.mmf_create(C.byref(cfg), C.byref(h)))
         self._h = h

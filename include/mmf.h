@@ -76,8 +76,8 @@ typedef struct mmf_config {
                               uint16 on host threads when every value is an integer in [0, 65534] (exactly, or the
                               chunk goes as float32), so that half the bytes cross PCIe; widened back on the device */
   int32_t host_threads;    /* threads of that narrowing pool (0 = half of the process's cores, at most 16) */
-  int32_t stream_solve;    /* series with gaps: 0 = automatic (solved by a consumer kernel running BESIDE the tcgen05 kernel
-                              for batches of >= 32,768 rows), 2 = always in a pass of their own after it */
+  int32_t stream_solve;    /* series with gaps: 0 = solved in a pass of their own after the tcgen05 kernel (default), 1 = by a
+                              consumer kernel launched BESIDE it (experimental: pays only with a register-capped build) */
   int32_t reserved1;
 } mmf_config;
 

@@ -478,3 +478,32 @@ def test_host_narrowing_is_exact_or_not_used():
                 assert n * t * 2 < r3["stats"].h2d_bytes < n * t * 4          # chunks 0-1 narrow, the rest float32
         eng.close()
     dev.close()
+
+
+def test_streaming_solve_matches_the_separate_pass():
+    """mmf_config.stream_solve = 1: the queued records of series with gaps are consumed by solve_stream_kernel while
+    the tcgen05 kernel is still producing them (release/acquire work list, PDL launch).  Same records, same arithmetic:
+    bit-equal forecasts and statuses to the default (a solve pass after the streaming kernel), also on a second call
+    (the work list must be left clean) and when the default path runs in between."""
+    import torch
+    n, t, h = 70_000, 400, 28
+    y, start = mmf.synth.daily_store_item_demand(n, t, seed=91, nan_frac=0.01)
+    y[5, :9] = np.nan                                         # general pass (fit_warp) queues a record of its own
+    y[6, :] = np.nan
+    yd = mmf.device_packed(y)
+    a = mmf.ForecastEngine()
+    b = mmf.ForecastEngine(stream_solve=True)
+    for eng in (a, b):
+        eng.plan_calendar(start, t, "D", h, "future")
+    want = a.fit_forecast(yd, t, h, want_status=True)
+    for rep in range(3):
+        got = b.fit_forecast(yd, t, h, want_status=True)
+        torch.cuda.synchronize()
+        assert torch.equal(got["status"], want["status"]), rep
+        assert np.array_equal(got["pred"].cpu().numpy(), want["pred"].cpu().numpy(), equal_nan=True), rep
+        if rep == 1:                                          # a small batch takes the default path on the same context
+            small = b.fit_forecast(yd[:1000], t, h)
+            torch.cuda.synchronize()
+            assert np.array_equal(small.cpu().numpy(), want["pred"][:1000].cpu().numpy(), equal_nan=True)
+    a.close()
+    b.close()
