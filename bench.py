@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--replicas", type=int, default=1,
                     help="single GPU diagnostic: store every forecast tile to this many LOCAL copies of the table through the "
                          "multi-destination epilogue (isolates its cost from NVLink)")
+    ap.add_argument("--stream-solve", action="store_true",
+                    help="experimental: solve the series with gaps beside the tcgen05 kernel (mmf_config.stream_solve = 1)")
     ap.add_argument("--no-traffic", action="store_true", help="skip the live ncu DRAM-traffic probe of the dominant kernel")
     ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--t", type=int, default=1095)
@@ -370,7 +372,7 @@ def run_ours(args):
         gather = "nccl-all_gather" if world > 1 else "none"
     mine = table[rank * n:(rank + 1) * n]
 
-    eng = mmf.ForecastEngine(device=local, kernel=args.kernel, tc_variant=args.tc_variant)
+    eng = mmf.ForecastEngine(device=local, kernel=args.kernel, tc_variant=args.tc_variant, stream_solve=args.stream_solve)
     # ForecastEngine enqueues on torch's current stream for CUDA tensors, so the CUDA events below see the kernels
     _, ps, npred = eng.plan_calendar(start, t, "D", h, args.mode)
     if args.mode == "holdout":

@@ -329,8 +329,36 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
           }
         }
       }
-      uint32_t hi[32], lo[32];
       const float2 c2 = make_float2(c, c);
+      const uint32_t a_hi = tmem_base + lane_addr + ASLOT_COL0 + (grp * ASLOTS + aslot) * 64;
+#ifdef MMF_TC_HALF_ST
+      // register diet (with -DMMF_TC_MAXNREG=80): the chunk leaves in two 16-column halves, so only 32 split values are
+      // live at a time instead of 64
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int q = half * 4 + q4;
+#pragma unroll
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            const float2 e = hlf ? make_float2(v[q].z, v[q].w) : make_float2(v[q].x, v[q].y);
+            const float2 rr = sub_f32x2(e, c2);
+            const uint32_t h0 = __float_as_uint(rr.x) & 0xFFFFE000u, h1 = __float_as_uint(rr.y) & 0xFFFFE000u;
+            const float2 l = sub_f32x2(rr, make_float2(__uint_as_float(h0), __uint_as_float(h1)));
+            hi[q4 * 4 + 2 * hlf] = h0;  hi[q4 * 4 + 2 * hlf + 1] = h1;
+            lo[q4 * 4 + 2 * hlf] = __float_as_uint(l.x);  lo[q4 * 4 + 2 * hlf + 1] = __float_as_uint(l.y);
+          }
+        }
+        if (half == 0) {
+          mbar_wait(bar_aempty(grp, aslot), aphase ^ 1u);   // MMAs that read this A slot have retired
+          tc_fence_after();
+        }
+        tmem_st_32x32b_x16(a_hi + half * 16, hi);
+        tmem_st_32x32b_x16(a_hi + 32 + half * 16, lo);
+      }
+#else
+      uint32_t hi[32], lo[32];
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
 #pragma unroll
@@ -345,9 +373,9 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
       }
       mbar_wait(bar_aempty(grp, aslot), aphase ^ 1u);   // MMAs that read this A slot have retired
       tc_fence_after();
-      const uint32_t a_hi = tmem_base + lane_addr + ASLOT_COL0 + (grp * ASLOTS + aslot) * 64;
       tmem_st_32x32b_x32(a_hi, hi);
       tmem_st_32x32b_x32(a_hi + 32, lo);
+#endif
       const bool last_own = collect && ch + NGROUPS >= tr.n_chunks;    // my last chunk of this tile
       if (last_own) {
         if ((nm & 3) != 0 && nm < SOLVE_SEG) {          // flush the partial group (right-aligned: oldest first)
