@@ -222,7 +222,10 @@ def run_reference(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{g} (store,item) groups x {t} days per step, {h}-day horizon, future mode "
                                    f"(bounded sample of the 1M-series workload)", "groups_per_step": g, "t": t,
-                       "horizon": h, "parallelism": f"cpu fan-out x{cores}"},
+                       "horizon": h, "parallelism": f"cpu fan-out x{cores}",
+                       "same_config_note": "same metric, series length, horizon and mode as the GPU arm; a bounded number "
+                                           f"of groups per step ({g} = 16 x cores): every group is an independent task of the "
+                                           "same size, so series/s of the fan-out does not depend on how many groups a step holds"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
