@@ -68,6 +68,8 @@ def parse():
                     help="replay each step as a CUDA graph (small batches are launch-bound); single GPU only")
     ap.add_argument("--pitch-floats", type=int, default=0,
                     help="row pitch of the device-resident y in floats (0 = T rounded up to 4; 32 | pitch = 128-B aligned rows)")
+    ap.add_argument("--no-others", action="store_true",
+                    help="skip the short extra measurements of the other BASELINE configurations (other_configs in the line)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-groups", type=int, default=0, help="groups per step of the reference arm (0 = 16 x cores)")
@@ -586,6 +588,64 @@ def run_ours(args):
             e2e["uint16_ingest"] = {"unavailable": str(exc)}
         eng2.close()
 
+    # ---- the other BASELINE configurations, measured briefly in the same run (single GPU, default workload only): the
+    # driver's record then also carries configs[1], configs[2], the reference's holdout contract and the gap path
+    others = None
+    default_run = (world == 1 and args.mode == "future" and args.nan_frac == 0.0 and args.calendars == 0 and args.replicas == 1
+                   and not args.graph and n == 1_000_000 and t == 1095)
+    if rank == 0 and default_run and not args.no_others:
+        def timed(call, bytes_per_step, steps=20, warm=3):
+            for _ in range(warm):
+                call()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                call()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            return {"ms_per_step": ms, "roofline_frac": bytes_per_step / (ms * 1e-3) / 1e9 / peak}
+
+        others = {}
+        try:
+            for name, ns in (("configs[1] 10k x 1095", 10_000), ("configs[2] 100k x 1095", 100_000)):
+                rot = int(min(64, -(-int(5 * 126e6) // (ns * t * 4))))
+                bufs = [mmf.device_packed(y[:ns], device=dev) for _ in range(rot)]       # distinct buffers: > 5x L2 in total
+                o = torch.empty((ns, h), device=dev)
+                k = [0]
+
+                def small():
+                    eng.fit_forecast(bufs[k[0] % rot], ps, npred, out=o)
+                    k[0] += 1
+                r = timed(small, ns * bytes_per_series, steps=50)
+                r.update({"series_per_s": ns / (r["ms_per_step"] * 1e-3), "rotating_buffers": rot})
+                others[name] = r
+                del bufs, o
+            # the reference's contract: hold out the last `horizon` rows, a value for every date (02:484-494)
+            engh = mmf.ForecastEngine(device=local, kernel=args.kernel)
+            _, psh, nph = engh.plan_calendar(start, t, "D", h, "holdout")
+            oh_ = torch.empty((n, (nph + 3) & ~3), device=dev)[:, :nph]
+            r = timed(lambda: engh.fit_forecast(y, psh, nph, out=oh_), n * (4 * (t - h) + 4 * t), steps=10)
+            r["series_per_s"] = n / (r["ms_per_step"] * 1e-3)
+            others["holdout mode, 1M x 1095 (a value for all 1095 dates)"] = r
+            del oh_
+            engh.close()
+            # series with gaps: 2 % of the values missing in every series
+            yn = y.clone() if y.is_contiguous() else mmf.device_packed(y, device=dev)
+            g2 = torch.Generator(device=dev).manual_seed(99)
+            for i0 in range(0, n, 1 << 18):
+                blk = yn[i0:i0 + (1 << 18)]
+                blk[torch.rand(blk.shape, generator=g2, device=dev) < 0.02] = float("nan")
+            r = timed(lambda: eng.fit_forecast(yn, ps, npred, out=mine), n * bytes_per_series, steps=10)
+            r["series_per_s"] = n / (r["ms_per_step"] * 1e-3)
+            others["2% of the values missing in every series, 1M x 1095"] = r
+            del yn
+            eng.fit_forecast(y, ps, npred, out=mine)           # leave the table as the main measurement wrote it
+            torch.cuda.synchronize()
+        except Exception as exc:          # noqa: BLE001 -- the extras must never take the main line down
+            others["error"] = repr(exc)
+
     cpu = None
     os.sched_setaffinity(0, all_cpus)                   # the CPU legs use every host core again
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -613,6 +673,7 @@ def run_ours(args):
                            "gather": gather, "gather_max_abs_diff_vs_nccl": gather_check},
                 **({"shard_only": shard_only} if shard_only is not None else {}),
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                **({"other_configs": others} if others is not None else {}),
                 "gpu_launches": launches_per_call * K, "clocks": clocks}
         print(json.dumps(line), flush=True)
     eng.close()
