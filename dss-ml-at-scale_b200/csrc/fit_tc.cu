@@ -168,7 +168,9 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
         mbar_init(bar_accempty(b), 4);    // 4 epilogue warps have read the accumulators
       }
       // gap counts of a tile: one arrival per transform warp that owns a chunk of it (release) -> epilogue (acquire)
-      for (int i = 0; i < NM_RING; ++i) mbar_init(bar_nm(i), n_chunks >= 2 ? 8 : 4);
+      // (every THREAD of those warps arrives, not one elected lane after a __syncwarp: the writer of each s_nm entry
+      //  then synchronises with its reader directly, which is also what compute-sanitizer's racecheck can follow)
+      for (int i = 0; i < NM_RING; ++i) mbar_init(bar_nm(i), n_chunks >= 2 ? 256 : 128);
       fence_mbar_init();
     }
     __syncwarp();
@@ -391,8 +393,8 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
       if (lane == 0) {
         mbar_arrive(bar_afull(grp, aslot));
         mbar_arrive(bar_empty(stage));                  // this warp's smem reads of the stage are done
-        if (last_own) mbar_arrive(bar_nm(lt & (NM_RING - 1)));     // releases this warp's s_nm entries to the epilogue
       }
+      if (last_own) mbar_arrive(bar_nm(lt & (NM_RING - 1)));       // releases this thread's s_nm entry to the epilogue
       stage += NGROUPS;
       if (stage >= STAGES) { stage -= STAGES; phase ^= 1u; }
       if (++aslot == ASLOTS) { aslot = 0; aphase ^= 1u; }

@@ -7,6 +7,8 @@
 // same float32 staging rows the kernels read.  The narrowing is exact or it is not used: a chunk in which any finite
 // value is not an integer in [0, 65534] is sent as float32 like before.  NaN / Inf (missing) -> 65535.
 #include <immintrin.h>
+#include <pthread.h>
+#include <sched.h>
 #include <stdint.h>
 
 #include <atomic>
@@ -80,10 +82,29 @@ bool narrow_rows(const float* src, int64_t ld_src, uint16_t* dst, int64_t ld_dst
 // A small persistent pool: the narrowing of one chunk is a parallel-for over row blocks.
 class NarrowPool {
  public:
-  explicit NarrowPool(int n_threads) : stop_(false), gen_(0), pending_(0) {
-    // workers are NOT pinned: several processes (one per GPU) may share a NUMA node's cores, and the scheduler spreads
-    // 16 runnable threads over idle cores by itself
-    for (int i = 0; i < n_threads; ++i) workers_.emplace_back([this] { loop(); });
+  NarrowPool(int n_threads, bool pin) : stop_(false), gen_(0), pending_(0) {
+    // Workers are pinned (one per CPU of the process's affinity mask, in mask order, the first CPU left to the caller)
+    // only when the caller says this process has the host to itself (pin == true: one GPU visible); several processes
+    // -- one per GPU -- share a NUMA node's cores and would all pick the same ones.
+    std::vector<int> cpus;
+    if (pin) {
+      cpu_set_t set;
+      if (sched_getaffinity(0, sizeof(set), &set) == 0)
+        for (int c = 0; c < CPU_SETSIZE; ++c)
+          if (CPU_ISSET(c, &set)) cpus.push_back(c);
+    }
+    for (int i = 0; i < n_threads; ++i) {
+      const int cpu = (int)cpus.size() > i + 1 ? cpus[i + 1] : -1;
+      workers_.emplace_back([this, cpu] {
+        if (cpu >= 0) {
+          cpu_set_t one;
+          CPU_ZERO(&one);
+          CPU_SET(cpu, &one);
+          pthread_setaffinity_np(pthread_self(), sizeof(one), &one);
+        }
+        loop();
+      });
+    }
   }
   ~NarrowPool() {
     {
@@ -162,7 +183,7 @@ class NarrowPool {
   std::atomic<bool> ok_{true};
 };
 
-NarrowPool* narrow_pool_create(int n_threads) { return new NarrowPool(n_threads > 0 ? n_threads : 1); }
+NarrowPool* narrow_pool_create(int n_threads, bool pin) { return new NarrowPool(n_threads > 0 ? n_threads : 1, pin); }
 void narrow_pool_destroy(NarrowPool* p) { delete p; }
 int narrow_pool_size(const NarrowPool* p) { return p ? p->size() + 1 : 0; }
 bool narrow_f32_to_u16(NarrowPool* p, const float* src, int64_t ld_src, uint16_t* dst, int64_t ld_dst, int64_t n, int32_t t,

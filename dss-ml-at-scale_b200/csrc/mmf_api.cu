@@ -22,7 +22,7 @@ using namespace mmf;
 // host_narrow.cpp: exact float32 -> uint16 narrowing of a chunk on a few host threads
 namespace mmf {
 class NarrowPool;
-NarrowPool* narrow_pool_create(int n_threads);
+NarrowPool* narrow_pool_create(int n_threads, bool pin);
 void narrow_pool_destroy(NarrowPool* p);
 int narrow_pool_size(const NarrowPool* p);
 bool narrow_f32_to_u16(NarrowPool* p, const float* src, int64_t ld_src, uint16_t* dst, int64_t ld_dst, int64_t n, int32_t t,
@@ -744,7 +744,11 @@ static int fit_forecast_impl(mmf_ctx* ctx, const void* y_any, int32_t dtype, int
         // conversion speeds up (profiles/r02/README.md)
         want = std::max(1, std::min(16, have / 2));
       }
-      ctx->narrow_pool = narrow_pool_create(want - 1);         // the calling thread is the last worker
+      int ndev_vis = 0;
+      if (cudaGetDeviceCount(&ndev_vis) != cudaSuccess) { cudaGetLastError(); ndev_vis = 0; }
+      bool pin = ndev_vis == 1;                                // this process has the host's cores to itself
+      if (const char* e = getenv("MMF_HOST_PIN")) pin = atoi(e) != 0;
+      ctx->narrow_pool = narrow_pool_create(want - 1, pin);    // the calling thread is the last worker
     }
     // rows per narrowed sub-chunk and store flavour: measured on the B200 box (16 threads, 1 M x 1,095 per step; float32
     // copies: 82.4 ms): 1,024 / 2,048 / 4,096 / 8,192 / 32,768 rows with ordinary stores 84.6 / 81.6 / 75.1 / 62.2 /
