@@ -113,6 +113,17 @@ struct MultiPlan {
   float* d_w = nullptr;                // zeros (beta is not offered for ragged batches)
   uint32_t* d_pending_by_cal = nullptr;
   alignas(64) unsigned char tmap_at[128];
+  // requests with many / per-calendar numbers of prediction rows (holdout: a value for every date of every calendar):
+  // fit kernels hand gamma / c to predict_tc_kernel<true>
+  bool many_pred = false;
+  int32_t n_pred_max = 0;
+  float* d_ap_hi = nullptr;            // [sum n_rows][P] tf32-hi / lo of the stacked whitened designs (B operand)
+  float* d_ap_lo = nullptr;
+  alignas(64) unsigned char tmap_bhi[128];
+  alignas(64) unsigned char tmap_blo[128];
+  PredUnit* d_units = nullptr;  size_t units_cap = 0;  int64_t n_units = 0;
+  unsigned char* d_tmaps_out = nullptr;
+  const void* key_out = nullptr;  int64_t key_ld_out = -1;
   // per-call tables, kept while the same buffer / row layout is fit again
   TileRec* d_tiles = nullptr;  size_t tiles_cap = 0;  int32_t n_tiles = 0;
   unsigned char* d_tmaps_y = nullptr;
@@ -183,6 +194,7 @@ namespace {
 void free_multi(MultiPlan& m) {
   cudaFree(m.d_cals); cudaFree(m.d_at); cudaFree(m.d_apred); cudaFree(m.d_a4); cudaFree(m.d_w);
   cudaFree(m.d_pending_by_cal); cudaFree(m.d_tiles); cudaFree(m.d_tmaps_y);
+  cudaFree(m.d_ap_hi); cudaFree(m.d_ap_lo); cudaFree(m.d_units); cudaFree(m.d_tmaps_out);
   m = MultiPlan{};
 }
 
@@ -923,20 +935,28 @@ int mmf_fit_forecast_int(mmf_ctx* ctx, const void* y, int32_t dtype, int64_t n, 
 
 // ---- ragged batches: many calendars, one launch ------------------------------------------------------------------
 int mmf_plan_calendars(mmf_ctx* ctx, const double* X_all, int32_t n_cal, const int32_t* n_rows, const int32_t* t_fit,
-                       const int32_t* pred_start, int32_t n_pred, int32_t p, int32_t has_constant) {
-  if (!ctx || !X_all || !n_rows || !t_fit || !pred_start) return fail(MMF_E_INVALID, "NULL argument");
+                       const int32_t* pred_start, const int32_t* n_pred_cal, int32_t p, int32_t has_constant) {
+  if (!ctx || !X_all || !n_rows || !t_fit || !pred_start || !n_pred_cal) return fail(MMF_E_INVALID, "NULL argument");
   if (n_cal < 1 || n_cal > 65535) return fail(MMF_E_INVALID, "n_cal=%d outside [1,65535]", n_cal);
   if (p < 1 || p > P) return fail(MMF_E_INVALID, "p=%d outside [1,%d]", p, P);
-  if (n_pred < 1 || n_pred > 64) return fail(MMF_E_UNSUPPORTED, "ragged batches forecast 1..64 rows per series (n_pred=%d)", n_pred);
+  // one common number of prediction rows <= 64: the forecasts are written by the fit kernel's own epilogue; anything
+  // else (holdout: every date of every calendar) goes through the tcgen05 predict kernel
+  bool many = false;
+  int32_t n_pred = n_pred_cal[0], n_pred_max = 0;
+  for (int c = 0; c < n_cal; ++c) {
+    if (n_pred_cal[c] < 1) return fail(MMF_E_INVALID, "calendar %d: n_pred=%d < 1", c, n_pred_cal[c]);
+    many = many || n_pred_cal[c] != n_pred || n_pred_cal[c] > 64;
+    n_pred_max = std::max(n_pred_max, n_pred_cal[c]);
+  }
   if (ctx->pinned > 0) return fail(MMF_E_UNSUPPORTED, "a captured CUDA graph pins this context");
   size_t total_rows = 0;
   int32_t tmax = 0, tmin = INT32_MAX;
   for (int c = 0; c < n_cal; ++c) {
     if (t_fit[c] < 33 || t_fit[c] > 65535 || n_rows[c] < t_fit[c])
       return fail(MMF_E_UNSUPPORTED, "calendar %d: need 33 <= t_fit <= 65535 and n_rows >= t_fit (t_fit=%d n_rows=%d)", c, t_fit[c], n_rows[c]);
-    if (pred_start[c] < 0 || pred_start[c] + n_pred > n_rows[c])
+    if (pred_start[c] < 0 || pred_start[c] + n_pred_cal[c] > n_rows[c])
       return fail(MMF_E_INVALID, "calendar %d: prediction rows [%d,%d) outside its %d design rows", c, pred_start[c],
-                  pred_start[c] + n_pred, n_rows[c]);
+                  pred_start[c] + n_pred_cal[c], n_rows[c]);
     total_rows += (size_t)n_rows[c];
     tmax = std::max(tmax, t_fit[c]);
     tmin = std::min(tmin, t_fit[c]);
@@ -947,7 +967,8 @@ int mmf_plan_calendars(mmf_ctx* ctx, const double* X_all, int32_t n_cal, const i
   CU_TRY(cudaStreamSynchronize(ctx->stream));
   free_multi(ctx->multi);
   MultiPlan& m = ctx->multi;
-  m.n_cal = n_cal; m.n_pred = n_pred; m.has_constant = has_constant ? 1 : 0;
+  m.n_cal = n_cal; m.n_pred = many ? 1 : n_pred; m.has_constant = has_constant ? 1 : 0;
+  m.many_pred = many; m.n_pred_max = n_pred_max;
   m.t_fit_max = tmax; m.t_pad_max = (tmax + 31) & ~31; m.min_chunks = (tmin + 31) / 32;
   m.cals.resize(n_cal);
   m.a4_off.resize(n_cal);
@@ -966,7 +987,7 @@ int mmf_plan_calendars(mmf_ctx* ctx, const double* X_all, int32_t n_cal, const i
     CalMeta& cm = m.cals[c];
     whiten_calendar(X, n_rows[c], p, t_fit[c], W, &cm.kept_mask, A);
     cm.t_fit = t_fit[c]; cm.n_chunks = (t_fit[c] + 31) / 32; cm.n_rows = n_rows[c];
-    cm.row_off = (int32_t)row_off; cm.pred_start = pred_start[c]; cm.n_pred = n_pred; cm.n_rows_pad = (n_rows[c] + 31) & ~31;
+    cm.row_off = (int32_t)row_off; cm.pred_start = pred_start[c]; cm.n_pred = n_pred_cal[c]; cm.n_rows_pad = (n_rows[c] + 31) & ~31;
     memcpy(apred.data() + row_off * P, A.data(), A.size() * sizeof(float));
     float* atc = at.data() + (size_t)c * 2 * P * m.t_pad_max;
     for (int32_t t = 0; t < t_fit[c]; ++t)
@@ -991,6 +1012,21 @@ int mmf_plan_calendars(mmf_ctx* ctx, const double* X_all, int32_t n_cal, const i
   CU_TRY(cudaMemset(m.d_w, 0, P * P * sizeof(float)));
   int rc = encode_2d(m.tmap_at, m.d_at, (uint64_t)m.t_pad_max, (uint64_t)n_cal * 2 * P, (uint64_t)m.t_pad_max * 4, 32, 2 * P);
   if (rc != MMF_OK) return rc;
+  if (many) {
+    // B operand of predict_tc_kernel: tf32-hi / lo of every calendar's whitened rows, stacked (+128 zero rows: the last
+    // chunk of the last calendar reads a full box)
+    std::vector<float> hi((total_rows + 128) * P, 0.f), lo((total_rows + 128) * P, 0.f);
+    for (size_t i = 0; i < total_rows * P; ++i) split_tf32(apred[i], &hi[i], &lo[i]);
+    CU_TRY(cudaMalloc(&m.d_ap_hi, hi.size() * sizeof(float)));
+    CU_TRY(cudaMalloc(&m.d_ap_lo, lo.size() * sizeof(float)));
+    CU_TRY(cudaMemcpy(m.d_ap_hi, hi.data(), hi.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(m.d_ap_lo, lo.data(), lo.size() * sizeof(float), cudaMemcpyHostToDevice));
+    rc = encode_2d(m.tmap_bhi, m.d_ap_hi, (uint64_t)P, (uint64_t)(total_rows + 128), (uint64_t)P * 4, P, 128, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc != MMF_OK) return rc;
+    rc = encode_2d(m.tmap_blo, m.d_ap_lo, (uint64_t)P, (uint64_t)(total_rows + 128), (uint64_t)P * 4, P, 128, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc != MMF_OK) return rc;
+    CU_TRY(cudaMalloc(&m.d_tmaps_out, (size_t)n_cal * 128));
+  }
   m.valid = true;
   return MMF_OK;
 }
@@ -1006,7 +1042,10 @@ int mmf_fit_forecast_ragged_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t
   for (int c = 0; c < m.n_cal; ++c)
     if (cal_row_start[c + 1] < cal_row_start[c]) return fail(MMF_E_INVALID, "cal_row_start must be non-decreasing");
   if (ld_y < m.t_fit_max) return fail(MMF_E_INVALID, "ld_y=%lld < the longest calendar's t_fit=%d", (long long)ld_y, m.t_fit_max);
-  if (ld_out != m.n_pred) return fail(MMF_E_INVALID, "ragged batches write a dense [n, n_pred] table (ld_out must equal n_pred=%d)", m.n_pred);
+  if (!m.many_pred && ld_out < m.n_pred) return fail(MMF_E_INVALID, "ld_out=%lld < n_pred=%d", (long long)ld_out, m.n_pred);
+  if (m.many_pred && (ld_out < m.n_pred_max || ld_out % 4 != 0))
+    return fail(MMF_E_INVALID, "this plan evaluates up to %d rows per series: ld_out must be >= that and a multiple of 4 (TMA stores)",
+                m.n_pred_max);
   if (stats) memset(stats, 0, sizeof(*stats));
   if (n == 0) return MMF_OK;
   if (n > (int64_t)0x7fffffff - 128) return fail(MMF_E_UNSUPPORTED, "n too large for 32-bit TMA coordinates");
@@ -1048,11 +1087,43 @@ int mmf_fit_forecast_ragged_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t
     m.key_y = y; m.key_n = n; m.key_ld = ld_y;
     m.key_rows.assign(cal_row_start, cal_row_start + m.n_cal + 1);
   }
+  if (m.many_pred && (m.key_out != out_pred || m.key_ld_out != ld_out || !same)) {
+    // work units of the predict kernel ((tile, chunk) pairs, a tile's chunks next to each other) and every calendar's
+    // view of the output table: its rows only, its n_pred columns only
+    std::vector<PredUnit> units;
+    std::vector<unsigned char> omaps((size_t)m.n_cal * 128);
+    for (int c = 0; c < m.n_cal; ++c) {
+      const CalMeta& cm = m.cals[c];
+      const int64_t r0 = cal_row_start[c], nr = cal_row_start[c + 1] - r0;
+      if (nr <= 0) { memset(omaps.data() + (size_t)c * 128, 0, 128); continue; }
+      int rc = encode_2d(omaps.data() + (size_t)c * 128, out_pred + r0 * ld_out, (uint64_t)cm.n_pred, (uint64_t)nr,
+                         (uint64_t)ld_out * 4, 32, 128);
+      if (rc != MMF_OK) return rc;
+      const int n_ch = (cm.n_pred + 127) / 128;
+      for (int64_t r = r0; r < r0 + nr; r += 128)
+        for (int ch = 0; ch < n_ch; ++ch)
+          units.push_back(PredUnit{(int32_t)r, (int32_t)std::min<int64_t>(128, r0 + nr - r), c, ch,
+                                   cm.row_off + cm.pred_start + ch * 128, (int32_t)(r - r0), {0, 0}});
+    }
+    int rc = grow((void**)&m.d_units, &m.units_cap, std::max<size_t>(1, units.size()) * sizeof(PredUnit));
+    if (rc != MMF_OK) return rc;
+    CU_TRY(cudaStreamSynchronize(s));
+    if (!units.empty()) CU_TRY(cudaMemcpy(m.d_units, units.data(), units.size() * sizeof(PredUnit), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(m.d_tmaps_out, omaps.data(), omaps.size(), cudaMemcpyHostToDevice));
+    m.n_units = (int64_t)units.size();
+    m.key_out = out_pred; m.key_ld_out = ld_out;
+  }
   // ---- scratch, counters
   const bool may_mask = !ctx->cfg.assume_finite;
   FitArgs a{};
   a.y = y; a.n = n; a.ld_y = ld_y; a.pred_start = 0; a.n_pred = m.n_pred; a.out = out_pred; a.ld_out = ld_out;
   a.status = status; a.n_out = 1;
+  if (m.many_pred) {
+    int rc = grow((void**)&ctx->d_gamma, &ctx->gamma_cap_bytes, (size_t)n * P * sizeof(float));
+    if (rc == MMF_OK) rc = grow((void**)&ctx->d_c, &ctx->c_cap_bytes, (size_t)n * sizeof(float));
+    if (rc != MMF_OK) return rc;
+    a.out_gamma = ctx->d_gamma; a.out_c = ctx->d_c; a.skip_pred = 1;
+  }
   if (may_mask) {
     int rc = grow((void**)&ctx->d_recs, &ctx->recs_cap_bytes, (size_t)n * sizeof(SolveRec));
     if (rc == MMF_OK) rc = grow((void**)&ctx->d_rec_rows, &ctx->rec_rows_cap_bytes, (size_t)n * sizeof(int64_t));
@@ -1101,12 +1172,21 @@ int mmf_fit_forecast_ragged_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t
         FitArgs ac = a;
         ac.y = y + r0 * ld_y; ac.n = nr; ac.out = out_pred + r0 * ld_out; ac.status = status + r0;
         ac.pred_start = cm.pred_start; ac.recs = a.recs + r0; ac.row_base = r0; ac.cal_id = c;
+        if (a.out_gamma != nullptr) { ac.out_gamma = a.out_gamma + r0 * P; ac.out_c = a.out_c + r0; }
         ac.only_pending = 1; ac.pending_count = nullptr;
         CU_TRY(launch_fit_warp(dc, ac, ctx->sm_count, s));
         ++launches;
       }
     }
     CU_TRY(launch_solve_rows(d, a, ctx->sm_count, s, m.d_cals));
+    ++launches;
+  }
+  if (m.many_pred) {
+    PredictLaunch pl;
+    memcpy(pl.tmap_bhi, m.tmap_bhi, 128);
+    memcpy(pl.tmap_blo, m.tmap_blo, 128);
+    memcpy(pl.tmap_out, m.tmap_bhi, 128);                  // unused by the ragged kernel (per-calendar maps instead)
+    CU_TRY(launch_predict_tc(d, a, pl, ctx->sm_count, s, m.d_units, m.n_units, m.d_tmaps_out));
     ++launches;
   }
   ctx->last_set = cs;

@@ -129,8 +129,18 @@ struct PredictLaunch {
   alignas(64) unsigned char tmap_blo[128];
   alignas(64) unsigned char tmap_out[128];
 };
+struct PredUnit {                          // one (tile, chunk) work unit of a ragged predict launch (32 B)
+  int32_t row0, nrows;                     // series rows of the tile inside one calendar
+  int32_t cal;                             // calendar: selects the output tensor map
+  int32_t ch;                              // 128-row chunk of that calendar's prediction rows
+  int32_t b_row;                           // first row of the chunk in the stacked (hi / lo) design tables
+  int32_t row_in_map;                      // row0 relative to the calendar's first row (outer coordinate of its map)
+  int32_t pad_[2];
+};
+static_assert(sizeof(PredUnit) == 32, "PredUnit is two 16-B loads");
 cudaError_t launch_predict_tc(const DesignView& d, const FitArgs& a, const PredictLaunch& pl, int sm_count,
-                              cudaStream_t s);
+                              cudaStream_t s, const PredUnit* units = nullptr, int64_t n_units_multi = 0,
+                              const unsigned char* tmaps_out = nullptr);
 
 // TMA + tcgen05/TMEM kernel (fully observed fast path).  `tmap_y` / `tmap_at` are CUtensorMap blobs.
 struct TcLaunch {

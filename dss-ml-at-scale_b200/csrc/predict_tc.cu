@@ -40,10 +40,26 @@ struct Smem {
   static constexpr int total = tmem_ptr + 16;
 };
 
+// MULTI: a ragged batch (mmf_fit_forecast_ragged_f32, holdout-style requests): the work units come from a table
+// (rows, calendar, chunk of THAT calendar's prediction rows, first row of the chunk in the stacked design table) and the
+// output goes through the calendar's own tensor map -- the table clipped to that calendar's rows and columns, so a tile
+// that straddles two calendars or a chunk that runs past the calendar's last date never writes outside its own block.
+template <bool MULTI>
 __global__ void __launch_bounds__(THREADS, 1)
 predict_tc_kernel(const __grid_constant__ PredictLaunch pl, const DesignView d, const FitArgs a, const int n_tiles,
-                  const int n_chunks) {
-  const int64_t n_units = (int64_t)n_tiles * n_chunks;
+                  const int n_chunks, const PredUnit* __restrict__ units, const unsigned char* __restrict__ tmaps_out,
+                  const int64_t n_units_multi) {
+  const int64_t n_units = MULTI ? n_units_multi : (int64_t)n_tiles * n_chunks;
+  auto unit_at = [&](int64_t u) -> PredUnit {
+    if (MULTI) {
+      const int4* p = reinterpret_cast<const int4*>(units + u);
+      const int4 v0 = __ldg(p), v1 = __ldg(p + 1);
+      return PredUnit{v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    }
+    const int tile = (int)(u / n_chunks), ch = (int)(u % n_chunks);
+    const int64_t left = a.n - (int64_t)tile * TILE_M;
+    return PredUnit{tile * TILE_M, (int)(left >= TILE_M ? TILE_M : left), 0, ch, a.pred_start + ch * TN, tile * TILE_M, 0, 0};
+  };
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   const uint32_t sbase = smem_u32(smem);
@@ -92,9 +108,8 @@ predict_tc_kernel(const __grid_constant__ PredictLaunch pl, const DesignView d, 
     int stage = 0;
     uint32_t phase = 0;
     for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
-      const int ch = (int)(u % n_chunks);
+      const int t0 = unit_at(u).b_row;
       mbar_wait(bar_bempty(stage), phase ^ 1u);
-      const int t0 = a.pred_start + ch * TN;
       tma_load_2d_x2_elect(bar_bfull(stage), B_STAGE_BYTES,
                            s_b + stage * B_STAGE_BYTES, pl.tmap_bhi, 0, t0, L2_EVICT_LAST,
                            s_b + stage * B_STAGE_BYTES + B_TILE_BYTES, pl.tmap_blo, 0, t0, L2_EVICT_LAST);
@@ -137,9 +152,10 @@ predict_tc_kernel(const __grid_constant__ PredictLaunch pl, const DesignView d, 
     for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++k) {
       const int ab = (int)(k & 1);
       const int lt = (int)k;
-      const int64_t row = (u / n_chunks) * TILE_M + r;
+      const PredUnit pu = unit_at(u);
+      const int64_t row = (int64_t)pu.row0 + r;
       float g[P];
-      if (row < a.n) {
+      if (r < pu.nrows) {
         const float4* gp = reinterpret_cast<const float4*>(a.out_gamma + row * P);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -180,9 +196,9 @@ predict_tc_kernel(const __grid_constant__ PredictLaunch pl, const DesignView d, 
     int64_t k = 0;                                         // unit counter: group g owns the units with k & 1 == g
     for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++k) {
       if ((int)(k & 1) != grp) continue;
-      const int tile = (int)(u / n_chunks), ch = (int)(u % n_chunks);
-      const int64_t row = (int64_t)tile * TILE_M + r;
-      const float c = (row < a.n) ? __ldg(a.out_c + row) : 0.f;
+      const PredUnit pu = unit_at(u);
+      const int64_t row = (int64_t)pu.row0 + r;
+      const float c = (r < pu.nrows) ? __ldg(a.out_c + row) : 0.f;
       mbar_wait(bar_dfull(grp), (uint32_t)((k >> 1) & 1));
       tc_fence_after();
       if (leader) bulk_wait_read_elect();                  // this group's previous stores have read the staging tile
@@ -206,9 +222,11 @@ predict_tc_kernel(const __grid_constant__ PredictLaunch pl, const DesignView d, 
       fence_proxy_async_smem();
       named_bar_sync(1 + grp, 128);
       if (leader) {
+        const void* tmo = MULTI ? static_cast<const void*>(tmaps_out + (size_t)pu.cal * 128) : static_cast<const void*>(pl.tmap_out);
+        if (MULTI) fence_tensormap_acquire(tmo);
 #pragma unroll
         for (int j = 0; j < TN / 32; ++j)
-          tma_store_2d_elect(pl.tmap_out, obase + j * OUT_SUB_BYTES, ch * TN + j * 32, tile * TILE_M);
+          tma_store_2d_elect(tmo, obase + j * OUT_SUB_BYTES, pu.ch * TN + j * 32, pu.row_in_map);
         bulk_commit_elect();
       }
     }
@@ -226,16 +244,24 @@ predict_tc_kernel(const __grid_constant__ PredictLaunch pl, const DesignView d, 
 }  // namespace
 
 cudaError_t launch_predict_tc(const DesignView& d, const FitArgs& a, const PredictLaunch& pl, int sm_count,
-                              cudaStream_t s) {
+                              cudaStream_t s, const PredUnit* units, int64_t n_units_multi, const unsigned char* tmaps_out) {
   if (a.n <= 0) return cudaSuccess;
+  const size_t smem = Smem::total + 1024;
+  if (units != nullptr) {
+    if (n_units_multi <= 0) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(predict_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int grid = n_units_multi < sm_count ? (int)n_units_multi : sm_count;
+    predict_tc_kernel<true><<<grid, THREADS, smem, s>>>(pl, d, a, 0, 1, units, tmaps_out, n_units_multi);
+    return cudaGetLastError();
+  }
   const int n_tiles = (int)((a.n + TILE_M - 1) / TILE_M);
   const int n_chunks = (a.n_pred + TN - 1) / TN;
-  const size_t smem = Smem::total + 1024;
-  cudaError_t e = cudaFuncSetAttribute(predict_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(predict_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int64_t n_units = (int64_t)n_tiles * n_chunks;
   const int grid = n_units < sm_count ? (int)n_units : sm_count;
-  predict_tc_kernel<<<grid, THREADS, smem, s>>>(pl, d, a, n_tiles, n_chunks);
+  predict_tc_kernel<false><<<grid, THREADS, smem, s>>>(pl, d, a, n_tiles, n_chunks, nullptr, nullptr, 0);
   return cudaGetLastError();
 }
 

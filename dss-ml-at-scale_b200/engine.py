@@ -243,38 +243,53 @@ class ForecastEngine:
         return self._calendar_plan
 
     # ---- ragged batches: many calendars, one launch ----------------------------------------------
-    def plan_calendars(self, starts, t_lens, freq: str = "D", horizon: int = 28, design: str = "trend_season_exog"):
-        """Plan ALL calendars of a ragged batch (future mode): calendar ``c`` starts at ``starts[c]`` and has
-        ``t_lens[c]`` grid rows; every series is fit on its whole history and forecast ``horizon`` rows past its end.
-        One host call whitens every calendar (``mmf_plan_calendars``); ``fit_forecast_ragged`` then fits all groups
-        in one kernel pass.  Returns the forecast dates per calendar, ``[n_cal, horizon]`` datetime64[D]."""
+    def plan_calendars(self, starts, t_lens, freq: str = "D", horizon: int = 28, design: str = "trend_season_exog",
+                       mode: str = "future"):
+        """Plan ALL calendars of a ragged batch: calendar ``c`` starts at ``starts[c]`` and has ``t_lens[c]`` grid rows.
+        ``mode="future"``: every series is fit on its whole history and forecast ``horizon`` rows past its end;
+        ``mode="holdout"`` (the reference's contract, 02:372-380 + 484-494): the last ``horizon`` rows are held out and a
+        value is produced for EVERY date of the calendar.  One host call whitens every calendar (``mmf_plan_calendars``);
+        ``fit_forecast_ragged`` then fits all groups in one pass of the tcgen05 kernel (+ one of the predict kernel in
+        holdout mode).  Returns the prediction dates per calendar: ``[n_cal, horizon]`` datetime64[D] (future) or a list
+        of ``t_lens[c]``-long arrays (holdout)."""
         starts = [np.datetime64(s, "D") for s in starts]
         t_lens = [int(t) for t in t_lens]
         if len(starts) != len(t_lens) or not starts:
             raise ValueError("starts and t_lens must have the same non-zero length")
-        blocks, dates = [], []
+        if mode not in ("future", "holdout"):
+            raise ValueError(f"mode must be 'holdout' or 'future', got {mode!r}")
+        blocks, dates, n_rows, t_fit, p_start, n_pred = [], [], [], [], [], []
         for st, tl in zip(starts, t_lens):
-            days = D.calendar_grid(st, tl + horizon, freq)
-            blocks.append(D.design_matrix(days, tl, design))
-            dates.append(np.asarray(days[tl:tl + horizon], dtype="datetime64[D]"))
+            if mode == "future":
+                days = D.calendar_grid(st, tl + horizon, freq)
+                tf, ps, npd = tl, tl, horizon
+            else:
+                if tl - horizon < 1:
+                    raise ValueError("series shorter than the forecast horizon")
+                days = D.calendar_grid(st, tl, freq)
+                tf, ps, npd = tl - horizon, 0, tl
+            blocks.append(D.design_matrix(days, tf, design))
+            dates.append(np.asarray(days[ps:ps + npd], dtype="datetime64[D]"))
+            n_rows.append(len(days)); t_fit.append(tf); p_start.append(ps); n_pred.append(npd)
         X = np.ascontiguousarray(np.concatenate(blocks, axis=0), dtype=np.float64)
-        n_rows = np.array([tl + horizon for tl in t_lens], dtype=np.int32)
-        t_fit = np.array(t_lens, dtype=np.int32)
-        N.check(self._lib.mmf_plan_calendars(self._h, X.ctypes.data, len(starts), n_rows.ctypes.data, t_fit.ctypes.data,
-                                             t_fit.ctypes.data, int(horizon), X.shape[1],
+        arr = [np.array(v, dtype=np.int32) for v in (n_rows, t_fit, p_start, n_pred)]
+        N.check(self._lib.mmf_plan_calendars(self._h, X.ctypes.data, len(starts), arr[0].ctypes.data, arr[1].ctypes.data,
+                                             arr[2].ctypes.data, arr[3].ctypes.data, X.shape[1],
                                              1 if D.design_has_constant(design) else 0))
-        self._ragged = (len(starts), int(horizon), int(max(t_lens)))
-        return np.stack(dates)
+        # (n_cal, columns of the output table, columns y must have)
+        self._ragged = (len(starts), int(max(n_pred)), int(max(t_fit)), mode)
+        return np.stack(dates) if mode == "future" else dates
 
     def fit_forecast_ragged(self, y, cal_row_start, out=None, status=None, want_status: bool = False,
                             want_stats: bool = False):
         """Fit a ragged batch: ``y`` [n, ld] float32 CUDA tensor whose rows are grouped by calendar -- calendar ``c``
-        owns rows ``[cal_row_start[c], cal_row_start[c+1])`` and reads columns ``[0, t_len_c)`` of them.  Returns the
-        dense ``[n, horizon]`` forecast table (or a dict with ``status`` / ``stats``)."""
+        owns rows ``[cal_row_start[c], cal_row_start[c+1])`` and reads columns ``[0, t_fit_c)`` of them.  Returns the
+        ``[n, horizon]`` forecast table (future mode) or ``[n, longest calendar]`` with a value for every date of each
+        row's own calendar and NaN beyond it (holdout mode) -- or a dict with ``status`` / ``stats``."""
         import torch
         if getattr(self, "_ragged", None) is None:
             raise RuntimeError("plan_calendars() must be called first")
-        n_cal, horizon, t_max = self._ragged
+        n_cal, n_out, t_max, mode = self._ragged
         yp, n, t_have, ld_y = _describe(y, "y")
         if not (_is_torch(y) and y.is_cuda and y.dtype == torch.float32) or t_have < t_max:
             raise ValueError(f"y must be a float32 CUDA tensor with at least {t_max} columns")
@@ -283,7 +298,10 @@ class ForecastEngine:
             raise ValueError("cal_row_start needs n_cal + 1 entries")
         self.set_stream(torch.cuda.current_stream(y.device).cuda_stream)
         if out is None:
-            out = torch.empty((n, horizon), device=y.device, dtype=torch.float32)
+            if mode == "future":
+                out = torch.empty((n, n_out), device=y.device, dtype=torch.float32)
+            else:       # holdout: [n, longest calendar]; columns beyond a row's own calendar stay NaN
+                out = torch.full((n, (n_out + 3) & ~3), float("nan"), device=y.device, dtype=torch.float32)[:, :n_out]
         if want_status and status is None:
             status = torch.empty(n, device=y.device, dtype=torch.int32)
         st = N.MmfStats() if want_stats else None

@@ -292,13 +292,14 @@ def pack_table_host(table, keys=DEFAULT_KEYS, date_col="Date", value_col="Demand
 
 
 # ---- the drop-in UDF ---------------------------------------------------------------------------
-RAGGED_MIN_BUCKETS = 2        # from this many calendars on, future-mode batches go through ONE ragged launch
+RAGGED_MIN_BUCKETS = 2        # from this many calendars on, a batch goes through ONE ragged launch
 
 
-def _fit_buckets_ragged(buckets, eng, freq, horizon, design, on_device):
+def _fit_buckets_ragged(buckets, eng, freq, horizon, mode, design, on_device):
     """All calendars of the batch in one launch (``mmf_plan_calendars`` + ``mmf_fit_forecast_ragged_f32``): the groups'
     rows are laid out calendar after calendar in one device buffer, each calendar's design is whitened in the same
-    host call, and one pass of the tcgen05 kernel fits every group against its own calendar (02:422-423 per group)."""
+    host call, and one pass of the tcgen05 kernel fits every group against its own calendar (02:422-423 per group);
+    in holdout mode one pass of the predict kernel then writes a value for every date of every group (02:484-494)."""
     import torch
 
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -308,18 +309,20 @@ def _fit_buckets_ragged(buckets, eng, freq, horizon, design, on_device):
     for i, b in enumerate(buckets):
         src = b.y if on_device else torch.from_numpy(b.y)
         y[int(rows[i]):int(rows[i + 1]), :b.t_len].copy_(src, non_blocking=True)
-    dates = eng.plan_calendars([b.start for b in buckets], [b.t_len for b in buckets], freq, horizon, design)
+    dates = eng.plan_calendars([b.start for b in buckets], [b.t_len for b in buckets], freq, horizon, design, mode)
     pred = eng.fit_forecast_ragged(y, rows).cpu().numpy()
     for i, b in enumerate(buckets):
         y_host = b.y.cpu().numpy() if on_device else b.y
-        yield b, dates[i], horizon, y_host, pred[int(rows[i]):int(rows[i + 1])]
+        n_pred = horizon if mode == "future" else b.t_len
+        yield b, dates[i], n_pred, y_host, np.ascontiguousarray(pred[int(rows[i]):int(rows[i + 1]), :n_pred])
 
 
 def _fit_buckets(buckets, eng, freq, horizon, mode, design, select, on_device):
     """Run the engine over every bucket: yields (bucket, out_days, n_pred, y_host, pred_host)."""
-    if (mode == "future" and select is None and len(buckets) >= RAGGED_MIN_BUCKETS and 1 <= horizon <= 64
-            and hasattr(eng, "fit_forecast_ragged") and all(33 <= b.t_len <= 65535 for b in buckets)):
-        yield from _fit_buckets_ragged(buckets, eng, freq, horizon, design, on_device)
+    t_fit_min = min((b.t_len - (horizon if mode == "holdout" else 0)) for b in buckets) if buckets else 0
+    if (select is None and len(buckets) >= RAGGED_MIN_BUCKETS and (mode == "holdout" or 1 <= horizon <= 64)
+            and hasattr(eng, "fit_forecast_ragged") and t_fit_min >= 33 and all(b.t_len <= 65535 for b in buckets)):
+        yield from _fit_buckets_ragged(buckets, eng, freq, horizon, mode, design, on_device)
         return
     for b in buckets:
         out_days, pred_start, n_pred = eng.plan_calendar(b.start, b.t_len, freq, horizon, mode, design)

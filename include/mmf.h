@@ -159,15 +159,19 @@ int mmf_fit_forecast_int(mmf_ctx* ctx, const void* y, int32_t dtype, int64_t n, 
  * costs a launch sequence per distinct calendar; a ragged plan whitens all calendars in one host call and ONE pass
  * of the tcgen05 kernel fits every group, each 128-row tile against its own calendar's design.
  *   X_all        the calendars' design matrices back to back: calendar c contributes n_rows[c] rows of p doubles
- *   t_fit[c]     fit rows of calendar c (33 .. 65535); rows [pred_start[c], pred_start[c] + n_pred) are evaluated
- *   n_pred       common to all calendars, 1 .. 64 (future mode: pred_start[c] = t_fit[c], n_pred = horizon)
+ *   t_fit[c]     fit rows of calendar c (33 .. 65535); rows [pred_start[c], pred_start[c] + n_pred[c]) are evaluated
+ *   n_pred[c]    per calendar.  One common value <= 64 (future mode: pred_start[c] = t_fit[c], n_pred[c] = horizon): the fit
+ *                kernel's own epilogue writes the forecasts.  Anything else (holdout, the reference's contract: pred_start[c]
+ *                = 0, n_pred[c] = every date of calendar c, 02:484-494): the fit hands gamma / c to the tcgen05 predict
+ *                kernel, which writes each calendar's block of the table through that calendar's own tensor map.
  * mmf_fit_forecast_ragged_f32: y [n, ld_y] device, rows grouped by calendar: calendar c owns rows
  * [cal_row_start[c], cal_row_start[c+1]) (host array of n_cal + 1 entries, 0 .. n); columns >= t_fit[c] of a row
- * are ignored; out_pred [n, n_pred] dense (ld_out == n_pred), device.  Enqueues on the ctx stream and synchronises
+ * are ignored; out_pred [n, ld_out] device, ld_out >= the largest n_pred[c] (and a multiple of 4 when the predict kernel
+ * writes it); columns beyond a row's own n_pred[c] are left untouched.  Enqueues on the ctx stream and synchronises
  * once (rows the streaming pass leaves to the general pass are counted per calendar on the host).
  * replaces: the same reference lines as mmf_plan_design / mmf_fit_forecast_f32, for all calendars of a batch.   */
 int mmf_plan_calendars(mmf_ctx* ctx, const double* X_all, int32_t n_cal, const int32_t* n_rows, const int32_t* t_fit,
-                       const int32_t* pred_start, int32_t n_pred, int32_t p, int32_t has_constant);
+                       const int32_t* pred_start, const int32_t* n_pred, int32_t p, int32_t has_constant);
 int mmf_fit_forecast_ragged_f32(mmf_ctx* ctx, const float* y, int64_t n, int64_t ld_y, const int64_t* cal_row_start,
                                 float* out_pred, int64_t ld_out, int32_t* out_status, mmf_stats* stats);
 

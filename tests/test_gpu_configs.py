@@ -507,3 +507,68 @@ def test_streaming_solve_matches_the_separate_pass():
             assert np.array_equal(small.cpu().numpy(), want["pred"][:1000].cpu().numpy(), equal_nan=True)
     a.close()
     b.close()
+
+
+def test_ragged_holdout_matches_oracle_and_per_bucket_calls():
+    """The reference's contract (hold out the last `horizon` rows, a value for EVERY date, 02:372-380 + 484-494) for a
+    batch whose groups sit on different calendars: one pass of the fit kernel + one of the predict kernel, each
+    calendar's block of the table written through its own tensor map (tiles that straddle two calendars, chunks that
+    run past a calendar's last date)."""
+    import torch
+    h = 28
+    cals, y, rows, ld = _ragged_case(seed=4)
+    eng = mmf.ForecastEngine()
+    dates = eng.plan_calendars([c[0] for c in cals], [c[1] for c in cals], "D", h, mode="holdout")
+    assert [len(d) for d in dates] == [c[1] for c in cals]
+    yd = torch.from_numpy(y).cuda()
+    res = eng.fit_forecast_ragged(yd, rows, want_status=True)
+    torch.cuda.synchronize()
+    pred, status = res["pred"].cpu().numpy(), res["status"].cpu().numpy()
+    assert pred.shape == (y.shape[0], max(c[1] for c in cals))
+    eng1 = mmf.ForecastEngine()
+    for ci, (start, t, n) in enumerate(cals):
+        r0, r1 = int(rows[ci]), int(rows[ci + 1])
+        yb = y[r0:r1, :t]
+        if t - h < 33:
+            continue                                            # (not in this case set)
+        grid = O.calendar_grid(start, t, "D")
+        want, wst, _, ratio = O.fit_forecast_packed(yb, O.design_matrix(grid, t - h), t - h, 0, t, return_gamma=True)
+        assert np.array_equal(status[r0:r1], wst), ci
+        assert np.isnan(pred[r0:r1, t:]).all()                  # columns beyond the calendar's own length stay NaN
+        ok = wst != 1
+        assert np.isnan(pred[r0:r1, :t][~ok]).all()
+        from conftest import forecast_leverage
+        lev = forecast_leverage(O.design_matrix(grid, t - h), t - h, 0, t)
+        tol = tolerance(yb, lev) / np.minimum(1.0, ratio[ok] / 0.25)
+        rel = np.abs(pred[r0:r1, :t][ok] - want[ok]).max(axis=1) / tol
+        _le(rel.max(), 1.0, f"calendar {ci}: t={t} n={n} leverage {lev:.3g}")
+        single = mmf.forecast_packed(mmf.device_packed(yb), start, "D", h, "holdout", engine=eng1).cpu().numpy()
+        assert np.array_equal(single, pred[r0:r1, :t], equal_nan=True), ci
+    eng.close()
+    eng1.close()
+
+
+def test_forecast_groups_many_calendars_holdout_mode_one_ragged_launch():
+    """DataFrame boundary, reference defaults (holdout): groups on different calendars == the per-group oracle UDF."""
+    import pandas as pd
+    rng = np.random.default_rng(8)
+    frames = []
+    for g in range(40):
+        t = int(rng.integers(80, 140))
+        start = np.datetime64("2020-01-06") + np.timedelta64(7 * int(rng.integers(0, 5)), "D")
+        days = start + np.arange(t) * np.timedelta64(7, "D")
+        vals = np.round(2000 + 3 * np.arange(t) + rng.normal(0, 25, t)).astype(np.float32)
+        keep = rng.random(t) > 0.03
+        keep[0] = keep[-1] = True
+        frames.append(pd.DataFrame({"Product": f"p{g % 4}", "SKU": f"s{g:03d}", "Date": days[keep].astype("datetime64[ns]"),
+                                    "Demand": vals[keep]}))
+    df = pd.concat(frames, ignore_index=True).sample(frac=1.0, random_state=2)
+    df["Date"] = df["Date"].dt.date
+    got = mmf.forecast_groups(df)                               # freq W-MON, horizon 40, holdout: 02:341, 526
+    want = O.fanout_apply(df, O.build_tune_and_score_model, ("Product", "SKU"))
+    assert len(got) == len(want)
+    assert (got["SKU"].to_numpy() == want["SKU"].to_numpy()).all()
+    assert (got["Date"].dt.date.to_numpy() == want["Date"].to_numpy()).all()
+    assert np.array_equal(got["Demand"].to_numpy(), want["Demand"].to_numpy(), equal_nan=True)
+    err = np.abs(got["Demand_Fitted"].to_numpy() - want["Demand_Fitted"].to_numpy())
+    _le(err.max(), 40 * tolerance(df["Demand"].to_numpy()), "ragged holdout DataFrame batch vs per-group oracle UDF")
