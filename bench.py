@@ -401,13 +401,13 @@ def run_ours(args):
 
     ragged_rows = None
     if args.calendars > 0:
-        if world > 1 or args.mode != "future":
-            raise SystemExit("--calendars is a single-GPU, future-mode option")
+        if world > 1:
+            raise SystemExit("--calendars is a single-GPU option")
         C_ = args.calendars
         ragged_rows = np.linspace(0, n, C_ + 1).astype(np.int64)
         starts = [np.datetime64(start, "D") - np.timedelta64(c, "D") for c in range(C_)]
         t0_plan = time.perf_counter()
-        eng.plan_calendars(starts, [t] * C_, "D", h)
+        eng.plan_calendars(starts, [t] * C_, "D", h, mode=args.mode)
         ragged_plan_s = time.perf_counter() - t0_plan
     reps = None
     if args.replicas > 1 and world == 1:

@@ -833,8 +833,8 @@ static int fit_forecast_impl(mmf_ctx* ctx, const void* y_any, int32_t dtype, int
         yk = s.d_y; ldk = pitch;
       } else if (y_dev) { yk = y + off * ld_y; ldk = ld_y; }
       else if (narrow && [&]() -> bool {
-                 // sub-chunk by sub-chunk: narrow into a (cache-resident) host slot, copy it into the chunk's device
-                 // staging; the narrowing of sub-chunk k+1 runs while the copy of sub-chunk k is in flight
+                 // sub-chunk by sub-chunk: narrow into a page-locked host slot, copy it into the chunk's device staging;
+                 // the narrowing of sub-chunk k+1 runs while the copy of sub-chunk k is in flight
                  if (it >= NBUF && cudaStreamWaitEvent(ctx->s_h2d, s.ev_comp, 0) != cudaSuccess) return false;   // device staging free
                  for (int64_t so = 0; so < m; so += sub_rows) {
                    const int64_t ms = std::min(sub_rows, m - so);

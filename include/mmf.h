@@ -167,7 +167,7 @@ int mmf_fit_forecast_int(mmf_ctx* ctx, const void* y, int32_t dtype, int64_t n, 
  * mmf_fit_forecast_ragged_f32: y [n, ld_y] device, rows grouped by calendar: calendar c owns rows
  * [cal_row_start[c], cal_row_start[c+1]) (host array of n_cal + 1 entries, 0 .. n); columns >= t_fit[c] of a row
  * are ignored; out_pred [n, ld_out] device, ld_out >= the largest n_pred[c] (and a multiple of 4 when the predict kernel
- * writes it); columns beyond a row's own n_pred[c] are left untouched.  Enqueues on the ctx stream and synchronises
+ * writes it); columns from the next multiple of 4 behind a row's own n_pred[c] on are left untouched (TMA stores clip with 16-byte granularity).  Enqueues on the ctx stream and synchronises
  * once (rows the streaming pass leaves to the general pass are counted per calendar on the host).
  * replaces: the same reference lines as mmf_plan_design / mmf_fit_forecast_f32, for all calendars of a batch.   */
 int mmf_plan_calendars(mmf_ctx* ctx, const double* X_all, int32_t n_cal, const int32_t* n_rows, const int32_t* t_fit,
