@@ -333,14 +333,14 @@ def test_integer_ingest_is_bit_equal_to_float32_ingest(dtype):
 
 
 # ---- ragged batches: groups on many calendars, ONE launch ---------------------------------------------------------
-def _ragged_case(seed=0):
+def _ragged_case(seed=0, short=64):
     """Calendars with different first dates AND lengths, group counts around the 128-row tile edge, rows with gaps,
     rows the streaming pass must hand to the general pass, an empty row; columns beyond a row's own length hold NaN
     on purpose (the per-calendar tensor maps must clip them away)."""
     import datetime as dt
     rng = np.random.default_rng(seed)
     cals = [(dt.date(2019, 1, 1), 400, 300), (dt.date(2019, 3, 5), 333, 127), (dt.date(2018, 7, 9), 365, 128),
-            (dt.date(2020, 2, 1), 97, 129), (dt.date(2019, 1, 2), 400, 1), (dt.date(2017, 12, 25), 64, 5),
+            (dt.date(2020, 2, 1), 97, 129), (dt.date(2019, 1, 2), 400, 1), (dt.date(2017, 12, 25), short, 5),
             (dt.date(2019, 6, 30), 250, 700)]
     t_max = max(t for _, t, _ in cals)
     ld = (t_max + 3) & ~3
@@ -517,7 +517,7 @@ def test_ragged_holdout_matches_oracle_and_per_bucket_calls():
     run past a calendar's last date)."""
     import torch
     h = 28
-    cals, y, rows, ld = _ragged_case(seed=4)
+    cals, y, rows, ld = _ragged_case(seed=4, short=150)       # (36 fit rows for 16 columns would be a coin toss in any precision)
     eng = mmf.ForecastEngine()
     dates = eng.plan_calendars([c[0] for c in cals], [c[1] for c in cals], "D", h, mode="holdout")
     assert [len(d) for d in dates] == [c[1] for c in cals]
