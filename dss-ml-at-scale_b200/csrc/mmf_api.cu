@@ -771,6 +771,8 @@ static int fit_forecast_impl(mmf_ctx* ctx, const void* y_any, int32_t dtype, int
     if (const char* e = getenv("MMF_HOST_SUB_ROWS")) sub_rows = std::max<int64_t>(64, atoll(e));   // tuning / experiments
     if (const char* e = getenv("MMF_HOST_STREAM_STORES")) stream_stores = atoi(e) != 0;
     sub_rows = std::min(sub_rows, chunk);
+    int direct_every = 5;
+    if (const char* e = getenv("MMF_HOST_DIRECT_EVERY")) direct_every = atoi(e);
     if (narrow) {
       for (int i = 0; i < NHOST && narrow; ++i) {
         HostSlot& hs = ctx->hslot[i];
@@ -832,7 +834,13 @@ static int fit_forecast_impl(mmf_ctx* ctx, const void* y_any, int32_t dtype, int
         ++launches;
         yk = s.d_y; ldk = pitch;
       } else if (y_dev) { yk = y + off * ld_y; ldk = ld_y; }
-      else if (narrow && [&]() -> bool {
+      else if ([&]() -> bool {
+                 // Every `direct_every`-th chunk crosses as float32 straight from the caller's buffer: the narrowing
+                 // threads are the slower of the two resources (they and the copy engine share the memory controllers),
+                 // so the link would otherwise idle a third of the time; a float32 chunk costs the link twice the bytes
+                 // but the host threads nothing.
+                 if (!narrow || (direct_every > 0 && (it % direct_every) == direct_every - 1)) return false;
+                 const bool ok = [&]() -> bool {
                  // sub-chunk by sub-chunk: narrow into a page-locked host slot, copy it into the chunk's device staging;
                  // the narrowing of sub-chunk k+1 runs while the copy of sub-chunk k is in flight
                  if (it >= NBUF && cudaStreamWaitEvent(ctx->s_h2d, s.ev_comp, 0) != cudaSuccess) return false;   // device staging free
@@ -848,6 +856,9 @@ static int fit_forecast_impl(mmf_ctx* ctx, const void* y_any, int32_t dtype, int
                    ++ctx->hslot_uses;
                  }
                  return true;
+               }();
+                 if (!ok) narrow = false;                   // a value uint16 cannot carry: float32 from here on
+                 return ok;
                }()) {
         CU_TRY(cudaEventRecord(s.ev_h2d, ctx->s_h2d));
         CU_TRY(cudaStreamWaitEvent(ctx->stream, s.ev_h2d, 0));
@@ -856,7 +867,6 @@ static int fit_forecast_impl(mmf_ctx* ctx, const void* y_any, int32_t dtype, int
         yk = s.d_y; ldk = pitch;
         h2d += m * (int64_t)pl.t_fit * 2;
       } else {
-        narrow = false;                                  // a value that uint16 cannot carry: float32 from here on
         if (it >= NBUF) CU_TRY(cudaStreamWaitEvent(ctx->s_h2d, s.ev_comp, 0));     // staging buffer free again
         if (ld_y == pitch)        // already pitched on the host: one contiguous copy (pad columns ride along, except
                                   // behind the caller's very last row, which may be the end of its buffer)

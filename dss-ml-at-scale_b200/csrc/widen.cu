@@ -23,49 +23,49 @@ __device__ __forceinline__ float widen_one(T x) {
   return static_cast<int32_t>(x) == Sentinel<T>::v ? __int_as_float(0x7fc00000) : static_cast<float>(x);
 }
 
-// 8 values per 16-B (int16) / 32-B (int32) load, two 16-B stores; every thread keeps UNROLL independent loads in
-// flight (a single load per trip left the kernel latency-bound at 1.3 TB/s: profiles/r02/ncu_widen.txt).  Rows are
-// walked with a pitch, so a group of 8 never straddles a row; the tail of a row (t % 8) takes the scalar path.
-constexpr int UNROLL = 4;
+// 8 values per 16-B (int16) / 32-B (int32) load, two 16-B stores.  A 64-thread quarter of the block owns a row at a time
+// and strides over its groups of 8 (no integer division per element: the first version computed row = i / groups in 64
+// bits for every group and ran at 1.3 TB/s whatever the unrolling, profiles/r02/ncu_widen*.txt); the loads of a row are
+// issued before its stores.  Rows are walked with a pitch, so a group never straddles a row; the tail of a row (t % 8)
+// takes the scalar path.
+constexpr int QUART = 64;                      // threads per row
+constexpr int ROWS_PER_BLOCK = TPB / QUART;    // 4 rows in flight per block
+constexpr int MAXG = 4;                        // groups of 8 per thread and row handled in registers (t <= 2,048), else looped
 
 template <typename T>
 __global__ void __launch_bounds__(TPB)
 widen_kernel(const T* __restrict__ src, int64_t ld_src, float* __restrict__ dst, int64_t ld_dst, int64_t n, int32_t t,
              int vec_ok) {
+  const int sub = threadIdx.x / QUART, lane = threadIdx.x % QUART;
   const int groups = (t + 7) >> 3;
-  const int64_t total = n * groups;
-  const int64_t stride = (int64_t)gridDim.x * TPB;
-  for (int64_t i0 = (int64_t)blockIdx.x * TPB + threadIdx.x; i0 < total; i0 += stride * UNROLL) {
-    T v[UNROLL][8];
-    int64_t row[UNROLL];
-    int c0[UNROLL];
-    bool vec[UNROLL];
+  for (int64_t row = (int64_t)blockIdx.x * ROWS_PER_BLOCK + sub; row < n; row += (int64_t)gridDim.x * ROWS_PER_BLOCK) {
+    const T* __restrict__ s = src + row * ld_src;
+    float* __restrict__ d = dst + row * ld_dst;
+    for (int g0 = 0; g0 < groups; g0 += QUART * MAXG) {
+      T v[MAXG][8];
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const int64_t i = i0 + u * stride;
-      row[u] = i < total ? i / groups : -1;
-      c0[u] = row[u] >= 0 ? (int)(i - row[u] * groups) << 3 : 0;
-      vec[u] = row[u] >= 0 && vec_ok && c0[u] + 8 <= t;
-      if (vec[u]) {
-        const T* __restrict__ s = src + row[u] * ld_src + c0[u];
-        if (sizeof(T) == 2) {
-          *reinterpret_cast<uint4*>(v[u]) = __ldcs(reinterpret_cast<const uint4*>(s));
-        } else {
-          reinterpret_cast<uint4*>(v[u])[0] = __ldcs(reinterpret_cast<const uint4*>(s));
-          reinterpret_cast<uint4*>(v[u])[1] = __ldcs(reinterpret_cast<const uint4*>(s) + 1);
+      for (int u = 0; u < MAXG; ++u) {
+        const int g = g0 + u * QUART + lane;
+        if (g < groups && vec_ok && (g << 3) + 8 <= t) {
+          if (sizeof(T) == 2) {
+            *reinterpret_cast<uint4*>(v[u]) = __ldcs(reinterpret_cast<const uint4*>(s + (g << 3)));
+          } else {
+            reinterpret_cast<uint4*>(v[u])[0] = __ldcs(reinterpret_cast<const uint4*>(s + (g << 3)));
+            reinterpret_cast<uint4*>(v[u])[1] = __ldcs(reinterpret_cast<const uint4*>(s + (g << 3)) + 1);
+          }
         }
       }
-    }
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      if (row[u] < 0) continue;
-      float* __restrict__ d = dst + row[u] * ld_dst + c0[u];
-      if (vec[u]) {
-        __stcs(reinterpret_cast<float4*>(d), make_float4(widen_one(v[u][0]), widen_one(v[u][1]), widen_one(v[u][2]), widen_one(v[u][3])));
-        __stcs(reinterpret_cast<float4*>(d + 4), make_float4(widen_one(v[u][4]), widen_one(v[u][5]), widen_one(v[u][6]), widen_one(v[u][7])));
-      } else {
-        const T* __restrict__ s = src + row[u] * ld_src + c0[u];
-        for (int k = 0; k < 8 && c0[u] + k < t; ++k) d[k] = widen_one(s[k]);
+      for (int u = 0; u < MAXG; ++u) {
+        const int g = g0 + u * QUART + lane;
+        if (g >= groups) continue;
+        const int c0 = g << 3;
+        if (vec_ok && c0 + 8 <= t) {
+          __stcs(reinterpret_cast<float4*>(d + c0), make_float4(widen_one(v[u][0]), widen_one(v[u][1]), widen_one(v[u][2]), widen_one(v[u][3])));
+          __stcs(reinterpret_cast<float4*>(d + c0 + 4), make_float4(widen_one(v[u][4]), widen_one(v[u][5]), widen_one(v[u][6]), widen_one(v[u][7])));
+        } else {
+          for (int k = 0; k < 8 && c0 + k < t; ++k) d[c0 + k] = widen_one(s[c0 + k]);
+        }
       }
     }
   }
@@ -76,8 +76,7 @@ cudaError_t launch(const void* src, int64_t ld_src, float* dst, int64_t ld_dst, 
   if (n <= 0 || t <= 0) return cudaSuccess;
   const int vec_ok = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0 && (ld_src * sizeof(T)) % 16 == 0 &&
                       (reinterpret_cast<uintptr_t>(dst) & 15u) == 0 && ld_dst % 4 == 0) ? 1 : 0;
-  const int64_t total = n * ((t + 7) >> 3);
-  const int64_t want = (total + (int64_t)TPB * UNROLL - 1) / ((int64_t)TPB * UNROLL), cap = (int64_t)sm * 16;
+  const int64_t want = (n + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK, cap = (int64_t)sm * 16;
   widen_kernel<T><<<(unsigned)(want < cap ? want : cap), TPB, 0, s>>>(static_cast<const T*>(src), ld_src, dst, ld_dst, n, t, vec_ok);
   return cudaGetLastError();
 }

@@ -102,7 +102,7 @@ def test_config5_10m_by_365_device_and_host_spill():
     res = eng2.fit_forecast(yh, ps, npred, out=oh, want_status=True, want_stats=True)
     # integer-valued demand: on a single-GPU host the path narrows each chunk to uint16 on the way (exactly), half the
     # bytes cross PCIe; with several GPUs visible automatic mode leaves the float32 copies alone
-    assert res["stats"].h2d_bytes in (n * t * 2, n * t * 4) and res["stats"].d2h_bytes >= n * h * 4
+    assert n * t * 2 <= res["stats"].h2d_bytes <= n * t * 4 and res["stats"].d2h_bytes >= n * h * 4
     assert int((res["status"] != 0).sum()) == 0
     got = torch.from_numpy(oh)
     ref = dev["pred"].cpu()
@@ -463,7 +463,10 @@ def test_host_narrowing_is_exact_or_not_used():
         res = eng.fit_forecast(yp, ps, npred, want_status=True, want_stats=True)
         wp, ws = device_result(y)
         assert np.array_equal(res["pred"], wp, equal_nan=True) and np.array_equal(res["status"], ws), (mode, chunk)
-        assert res["stats"].h2d_bytes == n * t * (2 if mode == "on" else 4), (mode, chunk)
+        # (every 5th chunk crosses as float32 on purpose: the link is the faster of the two resources, see mmf_api.cu)
+        direct_rows = sum(min(chunk, n - off) for it, off in enumerate(range(0, n, chunk)) if it % 5 == 4)
+        want_bytes = (n - direct_rows) * t * 2 + direct_rows * t * 4 if mode == "on" else n * t * 4
+        assert res["stats"].h2d_bytes == want_bytes, (mode, chunk)
         # pageable, unpitched rows narrow too
         res2 = eng.fit_forecast(np.ascontiguousarray(y), ps, npred)
         assert np.array_equal(res2, wp, equal_nan=True)
@@ -476,7 +479,7 @@ def test_host_narrowing_is_exact_or_not_used():
             wp3, _ = device_result(y2)
             assert np.array_equal(r3["pred"], wp3, equal_nan=True), (mode, chunk, badval)
             if mode == "on" and chunk == 700:
-                assert n * t * 2 < r3["stats"].h2d_bytes < n * t * 4          # chunks 0-1 narrow, the rest float32
+                assert r3["stats"].h2d_bytes == 1400 * t * 2 + (n - 1400) * t * 4     # chunks 0-1 narrow, the rest float32
         eng.close()
     dev.close()
 
