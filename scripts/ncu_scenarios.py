@@ -37,7 +37,9 @@ def main():
         prof.stop()
     elif what == "widen":
         y, start = mmf.synth.daily_store_item_demand_torch(n, t, seed=3)
-        yi = y.clamp(0, 32000).to(torch.int16).contiguous()
+        full = torch.zeros((n, 1096), dtype=torch.int16, device="cuda")     # 16-B row pitch: the vector path of the kernel
+        yi = full[:, :t]
+        yi.copy_(y.clamp(0, 32000).to(torch.int16))
         eng = mmf.ForecastEngine()
         _, ps, npred = eng.plan_calendar(start, t, "D", h, "future")
         eng.fit_forecast(yi, ps, npred)
