@@ -370,6 +370,66 @@ def _buckets_for(pdf, keys, date_col, value_col, freq, pack, eng):
     return pack_groups(pdf, keys, date_col, value_col, freq)
 
 
+SINGLE_GROUP_MAX_ROWS = 4096
+
+
+def _single_group_fast(pdf, keys, date_col, value_col, freq, horizon, mode, design, eng, null_keys_on_gaps):
+    """The literal drop-in -- ``applyInPandas`` hands over ONE group per call (02:523-528) -- without the machinery
+    that many groups need (key factorisation, bucket bookkeeping, a key frame): returns the output frame, or None
+    when the frame holds more than one group (or null keys) and the general path must run.  Same rows, dtypes and
+    values as the general path (tests compare them)."""
+    n = len(pdf)
+    if n == 0 or n > SINGLE_GROUP_MAX_ROWS:
+        return None
+    key_cols = []
+    for k in keys:
+        col = pdf[k]
+        vals = col.to_numpy()
+        first = vals[0]
+        if first is None or first != first or not (vals == first).all():
+            return None
+        key_cols.append(col)
+    dvals = pdf[date_col].to_numpy()
+    if dvals.dtype.kind == "M":
+        days = dvals.astype("datetime64[D]").astype(np.int64)
+    elif dvals.dtype == object and n and hasattr(dvals[0], "toordinal"):
+        days = np.fromiter((d.toordinal() for d in dvals), dtype=np.int64, count=n) - 719163    # 1970-01-01
+    else:
+        days = D.as_days(dvals).astype(np.int64)
+    vals = pdf[value_col].to_numpy(dtype=np.float32, na_value=np.nan)
+    step = D.FREQ_DAYS[freq]
+    d0, d1 = int(days.min()), int(days.max())
+    if freq == "W-MON" and (d0 + 3) % 7 != 0:
+        raise ValueError("W-MON series must start on a Monday")
+    t_len = (d1 - d0) // step + 1
+    off = days - d0
+    pos = off // step
+    if step > 1:
+        on = off % step == 0
+        if not on.all():
+            pos, vals = pos[on], vals[on]
+    y = np.full((1, (t_len + 3) & ~3), np.nan, dtype=np.float32)[:, :t_len]
+    seen = np.zeros(t_len, dtype=bool)
+    seen[pos] = True
+    if int(seen.sum()) != pos.size:            # the reference's set_index("Date").asfreq() raises here too (02:423)
+        raise ValueError(f"cannot reindex on an axis with duplicate labels: {pos.size - int(seen.sum())} rows repeat "
+                         f"a (group, date) combination")
+    y[0, pos] = vals
+    out_days, pred_start, n_pred = eng.plan_calendar(np.datetime64(d0, "D"), int(t_len), freq, horizon, mode, design)
+    pred = eng.fit_forecast(y, pred_start, n_pred)
+    take0 = np.zeros(n_pred, dtype=np.intp)
+    frame = {k: pd.Series(c.array.take(take0), dtype=c.dtype, copy=False) for k, c in zip(keys, key_cols)}
+    frame[date_col] = np.asarray(out_days).astype("datetime64[ns]")
+    frame[value_col] = np.ascontiguousarray(y[0]) if mode == "holdout" else np.full(n_pred, np.nan, dtype=np.float32)
+    frame[value_col + "_Fitted"] = np.asarray(pred).reshape(-1)
+    if null_keys_on_gaps and mode == "holdout":
+        gap = np.isnan(frame[value_col])
+        if gap.any():
+            for k in keys:
+                frame[k] = frame[k].astype(object).where(~gap, None)
+    return pd.DataFrame(frame)
+
+
 def forecast_groups(pdf, *, keys=DEFAULT_KEYS, date_col="Date", value_col="Demand",
                     freq="W-MON", horizon=FORECAST_HORIZON, mode="holdout", design="trend_season_exog",
                     engine: ForecastEngine | None = None, pack: str = "host", select=None,
@@ -397,6 +457,10 @@ def forecast_groups(pdf, *, keys=DEFAULT_KEYS, date_col="Date", value_col="Deman
     eng = engine or default_engine()
     keys = list(keys)
     fitted_col = value_col + "_Fitted"
+    if pack == "host" and select is None and isinstance(pdf, pd.DataFrame):
+        one = _single_group_fast(pdf, keys, date_col, value_col, freq, horizon, mode, design, eng, null_keys_on_gaps)
+        if one is not None:
+            return one
     buckets = _buckets_for(pdf, keys, date_col, value_col, freq, pack, eng)
     parts, lengths = [], []
     for b, out_days, n_pred, y_host, pred in _fit_buckets(buckets, eng, freq, horizon, mode, design, select, pack == "device"):

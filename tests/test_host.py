@@ -194,3 +194,44 @@ def test_duplicate_dates_raise_like_asfreq():
         mmf.pack_groups(df, freq="W-MON", pinned=False)
     with pytest.raises(ValueError, match="duplicate"):
         mmf.frames.pack_table_host(pa.Table.from_pandas(df, preserve_index=False), freq="W-MON", pinned=False)
+
+
+def test_single_group_fast_path_equals_general_path():
+    """The literal drop-in (one group per call, 02:527) takes a short cut around the many-groups machinery; it must
+    return exactly what the general path returns: gaps, off-grid rows, unsorted input, both modes, null keys on gaps,
+    non-string keys, datetime64 dates; more than one group or a null key falls through to the general path."""
+    from mmf import frames as F
+    df = mmf.synth.reference_weekly_demand(n_skus=2)
+    sku = df["SKU"].iloc[0]
+    one = df[df["SKU"] == sku].copy()
+    one = one[one["Date"] != dt.date(2019, 5, 6)]                                           # a gap
+    extra = pd.DataFrame([(one["Product"].iloc[0], sku, dt.date(2019, 5, 8), 123.0)], columns=one.columns)
+    one = pd.concat([one, extra.astype({"Demand": np.float32})]).sample(frac=1.0, random_state=1)   # off-grid row, shuffled
+    as_ts = one.assign(Date=pd.to_datetime(one["Date"]))                                    # datetime64 dates
+    num = one.assign(Product=7, SKU=np.int64(42))                                           # numeric keys
+    eng = _OracleEngine()
+
+    def both(frame, **kw):
+        fast = mmf.forecast_groups(frame, engine=eng, **kw)
+        keep, F.SINGLE_GROUP_MAX_ROWS = F.SINGLE_GROUP_MAX_ROWS, 0
+        try:
+            general = mmf.forecast_groups(frame, engine=eng, **kw)
+        finally:
+            F.SINGLE_GROUP_MAX_ROWS = keep
+        pd.testing.assert_frame_equal(fast, general)
+        return fast
+
+    for frame in (one, as_ts, num):
+        for kw in ({}, {"mode": "future", "horizon": 8}, {"null_keys_on_gaps": True}, {"design": "exog_only"}):
+            out = both(frame, **kw)
+            assert len(out) == (157 if kw.get("mode") != "future" else 8)
+    assert F._single_group_fast(df, ["Product", "SKU"], "Date", "Demand", "W-MON", 40, "holdout", "trend_season_exog",
+                                eng, False) is None                                         # two groups: general path
+    nul = one.assign(SKU=None)
+    assert F._single_group_fast(nul, ["Product", "SKU"], "Date", "Demand", "W-MON", 40, "holdout", "trend_season_exog",
+                                eng, False) is None
+    with pytest.raises(ValueError, match="duplicate"):
+        mmf.forecast_groups(pd.concat([one, one.iloc[[3]]]), engine=eng)
+    daily = pd.DataFrame({"store": "a", "item": "b", "d": pd.date_range("2021-03-01", periods=90, freq="D"),
+                          "q": np.arange(90, dtype=np.float32)})
+    both(daily, keys=("store", "item"), date_col="d", value_col="q", freq="D", horizon=14, mode="future")
