@@ -386,7 +386,10 @@ def _single_group_fast(pdf, keys, date_col, value_col, freq, horizon, mode, desi
         col = pdf[k]
         vals = col.to_numpy()
         first = vals[0]
-        if first is None or first != first or not (vals == first).all():
+        if pd.isna(first):
+            return None                                   # null keys: the general path (a null key is its own group)
+        same = vals == first
+        if not (isinstance(same, np.ndarray) and same.dtype == bool and same.all()):
             return None
         key_cols.append(col)
     dvals = pdf[date_col].to_numpy()
