@@ -621,7 +621,7 @@ def run_ours(args):
                 r = timed(small, ns * bytes_per_series, steps=50)
                 r.update({"series_per_s": ns / (r["ms_per_step"] * 1e-3), "rotating_buffers": rot})
                 # the same batch when the caller vouches for gap-free data (mmf_config.assume_finite: no fix-up launches)
-                engf = mmf.ForecastEngine(device=local, kernel=args.kernel, assume_finite=True)
+                engf = mmf.ForecastEngine(device=local, kernel=args.kernel, assume_finite=True, tc_variant=args.tc_variant)
                 engf.plan_calendar(start, t, "D", h, "future")
 
                 def small_finite():

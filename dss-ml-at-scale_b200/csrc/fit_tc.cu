@@ -104,16 +104,30 @@ __device__ __forceinline__ float centring_constant(const float* __restrict__ yro
 #else
 #define MMF_TC_KERNEL_ATTR __launch_bounds__(THREADS, 1)
 #endif
-template <int STAGES, int OBUF, bool MULTI>
+// BAL (tc_variant = 3, an experiment): a balanced launch -- instead of dealing 128-row tiles round robin (79 tiles
+// leave 69 of the 148 SMs idle), every CTA owns one contiguous range of mv.bal_rows rows (a multiple of 8) and walks it in 128-row tiles; the
+// range's last tile is short and is loaded as 8-row boxes, so no SM streams rows it does not own.
+// Rows are independent in the GEMM, so the forecasts are bit-identical to the round-robin launch's.
+template <int STAGES, int OBUF, bool MULTI, bool BAL>
 __global__ void MMF_TC_KERNEL_ATTR
 fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const FitArgs a,
-              uint32_t* __restrict__ pending_count, const int n_tiles, const int n_chunks, const MultiView mv) {
+              uint32_t* __restrict__ pending_count, const int n_tiles_all, const int n_chunks, const MultiView mv) {
+  static_assert(!(MULTI && BAL), "ragged launches carry their own tile table");
   using SmemLayout = SmemLayoutT<STAGES, OBUF>;
+  // BAL: this CTA's rows; its k-th tile keeps the round-robin loop index blockIdx.x + k * gridDim.x
+  const int64_t cta_row0 = BAL ? (int64_t)blockIdx.x * mv.bal_rows : 0;
+  const int cta_rows = BAL ? (int)(a.n - cta_row0 < mv.bal_rows ? a.n - cta_row0 : mv.bal_rows) : 0;
+  const int n_tiles = BAL ? (int)blockIdx.x + ((cta_rows + TILE_M - 1) / TILE_M) * (int)gridDim.x : n_tiles_all;
   auto tile_rec = [&](int ti) -> TileRec {
     if (MULTI) {
       if (ti >= n_tiles) return TileRec{0, 0, 0, 1};
       const int4 v = __ldg(reinterpret_cast<const int4*>(mv.tiles) + ti);
       return TileRec{v.x, v.y, v.z, v.w};
+    }
+    if (BAL) {
+      const int k = ti / (int)gridDim.x;
+      const int left = cta_rows - k * TILE_M;
+      return TileRec{(int)cta_row0 + k * TILE_M, left >= TILE_M ? TILE_M : (left > 0 ? left : 0), 0, n_chunks};
     }
     const int64_t left = a.n - (int64_t)ti * TILE_M;
     return TileRec{ti * TILE_M, (int)(left >= TILE_M ? TILE_M : (left > 0 ? left : 0)), 0, n_chunks};
@@ -180,6 +194,7 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
     if (lane == 0) {
       prefetch_tensormap(tl.tmap_y);
       prefetch_tensormap(tl.tmap_at);
+      if (BAL) prefetch_tensormap(tl.tmap_y8);
     }
   } else if (warp >= WARP_EPI0 && warp < WARP_PROD) {
     // prediction rows of the whitened design -> shared (broadcast-read in the epilogue); ragged launches reload
@@ -211,6 +226,22 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
       const void* tmy = MULTI ? static_cast<const void*>(mv.tmaps_y + (size_t)tr.cal * 128) : static_cast<const void*>(tl.tmap_y);
       if (MULTI && tr.cal != last_cal) { fence_tensormap_acquire(tmy); last_cal = tr.cal; }
       const int at_row = MULTI ? tr.cal * 2 * P : 0;
+      if (BAL && tr.nrows < TILE_M) {
+        // short tile: the design box as usual, the series rows as 8-row boxes (same swizzled layout: a box is one
+        // 1,024-B swizzle atom of the stage); rows beyond the tile keep whatever the stage held -- their lanes compute
+        // garbage that nobody reads.  A box that crosses the end of the buffer is zero-filled and still counts in full.
+        const int nb = (tr.nrows + 7) >> 3;
+        for (int ch = 0; ch < tr.n_chunks; ++ch) {
+          mbar_wait(bar_empty(stage), phase ^ 1u);
+          mbar_expect_tx_elect(bar_full(stage), static_cast<uint32_t>(nb) * 1024u + AT_STAGE_BYTES);
+          tma_issue_2d_elect(bar_full(stage), s_at + stage * AT_STAGE_BYTES, tl.tmap_at, ch * KC, 0, L2_EVICT_LAST);
+          for (int j = 0; j < nb; ++j)
+            tma_issue_2d_elect(bar_full(stage), s_y + stage * Y_STAGE_BYTES + j * 1024, tl.tmap_y8, ch * KC,
+                               tr.row0 + 8 * j, L2_EVICT_FIRST);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        continue;
+      }
       for (int ch = 0; ch < tr.n_chunks; ++ch) {
         mbar_wait(bar_empty(stage), phase ^ 1u);
         tma_load_2d_x2_elect(bar_full(stage), Y_STAGE_BYTES + AT_STAGE_BYTES,
@@ -298,8 +329,8 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
       float4 v[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) v[q] = lds128(rowp + ((static_cast<uint32_t>(q) ^ sw) << 4));
-      // (ragged: rows of a partial tile beyond the calendar's last row belong to the NEXT tile -- never touch their records)
-      if (collect && (!MULTI || r < tr.nrows)) {
+      // (ragged / balanced: rows of a short tile beyond its last row belong to ANOTHER tile -- never touch their records)
+      if (collect && (!(MULTI || BAL) || r < tr.nrows)) {
         float2 chk2 = make_float2(0.f, 0.f);            // 0 * x is NaN exactly when x is NaN or Inf
         const float2 zero2 = make_float2(0.f, 0.f);
 #pragma unroll
@@ -320,7 +351,10 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
           }
           // positions are shifted into a 64-bit register and leave four at a time (one 8-B store, the unit the
           // solve kernel reads): a 2-B store per gap made the record traffic the limiter of the gappy case
-          uint16_t* __restrict__ mt = a.recs[(int64_t)tr.row0 + r].miss_t + grp * SOLVE_SEG;
+          // segment = parity of the chunk inside the TILE (all of a group's chunks of one tile share it), not the group:
+          // with an odd chunk count the groups swap roles from tile to tile, and the order in which the solve applies
+          // the gaps -- hence the forecast's last bits -- must not depend on where in a launch the series sits
+          uint16_t* __restrict__ mt = a.recs[(int64_t)tr.row0 + r].miss_t + (ch & 1) * SOLVE_SEG;
           const int tbase = ch * KC;
           while (gaps) {
             const int pos = __ffs(gaps) - 1;
@@ -381,11 +415,11 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
       const bool last_own = collect && ch + NGROUPS >= tr.n_chunks;    // my last chunk of this tile
       if (last_own) {
         if ((nm & 3) != 0 && nm < SOLVE_SEG) {          // flush the partial group (right-aligned: oldest first)
-          uint16_t* __restrict__ mt = a.recs[(int64_t)tr.row0 + r].miss_t + grp * SOLVE_SEG;
+          uint16_t* __restrict__ mt = a.recs[(int64_t)tr.row0 + r].miss_t + (ch & 1) * SOLVE_SEG;
           *reinterpret_cast<unsigned long long*>(mt + (nm & ~3)) = packq >> (16 * (4 - (nm & 3)));
         }
         const int cnt = nm > 0x7ffe ? 0x7ffe : nm;
-        s_nm[((lt & (NM_RING - 1)) * NGROUPS + grp) * TILE_M + r] = static_cast<uint16_t>(cnt | (bad ? 0x8000 : 0));
+        s_nm[((lt & (NM_RING - 1)) * NGROUPS + (ch & 1)) * TILE_M + r] = static_cast<uint16_t>(cnt | (bad ? 0x8000 : 0));
       }
       tmem_wait_st();
       tc_fence_before();
@@ -454,14 +488,14 @@ fit_tc_kernel(const __grid_constant__ TcLaunch tl, const DesignView d, const Fit
       tc_fence_after();
       uint32_t acc[32];
       tmem_ld_32x32b_x32(tmem_base + lane_addr + ACC_COL0 + ab * 32, acc);
-      // gaps seen by the two transform groups in this tile (a group owns no chunk of it only when n_chunks == 1)
+      // gaps the transform groups saw in this tile, by chunk parity
       int nm0 = 0, nm1 = 0;
       bool general = false;
       if (collect) {
         mbar_wait(bar_nm(lt & (NM_RING - 1)), (lt / NM_RING) & 1);     // acquire the transform warps' counts
         const uint16_t* nmrow = s_nm + (lt & (NM_RING - 1)) * NGROUPS * TILE_M + r;
-        const bool has0 = n_chunks >= 2 || ((lt * n_chunks) & 1) == 0;      // (ragged launches: every calendar has >= 2 chunks)
-        const bool has1 = n_chunks >= 2 || ((lt * n_chunks) & 1) == 1;
+        const bool has0 = true;                 // entry 0: gaps in the tile's even chunks, entry 1: in its odd chunks
+        const bool has1 = n_chunks >= 2;        // (a one-chunk calendar has no odd chunk; ragged launches: always >= 2)
         const unsigned f0 = has0 ? nmrow[0] : 0u, f1 = has1 ? nmrow[TILE_M] : 0u;
         nm0 = f0 & 0x7fff; nm1 = f1 & 0x7fff;
         // mostly-missing rows: the downdate I - sum a a^T cancels catastrophically; fit_warp builds their Gram
@@ -614,15 +648,27 @@ bool fit_tc_supported(const DesignView& d, const FitArgs& a, const char** why) {
   return w == nullptr;
 }
 
-template <int STAGES, int OBUF, bool MULTI>
+template <int STAGES, int OBUF, bool MULTI, bool BAL = false>
 static cudaError_t launch_variant(const DesignView& d, const FitArgs& a, const TcLaunch& tl, uint32_t* pending_count,
                                   int sm_count, cudaStream_t s, int n_tiles, int n_chunks, const MultiView& mv) {
   const size_t smem = SmemLayoutT<STAGES, OBUF>::total + 1024;
-  cudaError_t e = cudaFuncSetAttribute(fit_tc_kernel<STAGES, OBUF, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(fit_tc_kernel<STAGES, OBUF, MULTI, BAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const int grid = n_tiles < sm_count ? n_tiles : sm_count;
-  fit_tc_kernel<STAGES, OBUF, MULTI><<<grid, THREADS, smem, s>>>(tl, d, a, pending_count, n_tiles, n_chunks, mv);
+  const int grid = BAL ? (int)((a.n + mv.bal_rows - 1) / mv.bal_rows) : (n_tiles < sm_count ? n_tiles : sm_count);
+  fit_tc_kernel<STAGES, OBUF, MULTI, BAL><<<grid, THREADS, smem, s>>>(tl, d, a, pending_count, n_tiles, n_chunks, mv);
   return cudaGetLastError();
+}
+
+// Rows per CTA of a balanced launch (0: deal 128-row tiles round robin).  An experiment that did not pay, built only for
+// tc_variant = 3: with more than one tile per CTA the short tile costs almost a whole tile's
+// pipeline time on EVERY SM, where the round-robin deal leaves the extra tile to a few (100 k series 100.5 -> 103.7 us,
+// 125 k 113.9 -> 121.3 us); a batch of less than one wave (10 k series: 79 tiles -> 139 CTAs x 72 rows) gains 6 % when
+// steps are timed one by one (41.0 -> 38.4 us) and LOSES 30 % when they run back to back (24.0 -> 31.1 us): the idle SMs
+// of the 79-CTA launch are where the next call's kernels start.
+int fit_tc_balanced_rows(int64_t n, int sm_count, int variant) {
+  if (variant != 3) return 0;
+  const int64_t per = (n + sm_count - 1) / sm_count;
+  return (int)((per + 7) / 8 * 8);
 }
 
 cudaError_t launch_fit_tc(const DesignView& d, const FitArgs& a, const TcLaunch& tl, uint32_t* pending_count,
@@ -638,6 +684,12 @@ cudaError_t launch_fit_tc(const DesignView& d, const FitArgs& a, const TcLaunch&
   // is bound by HBM writes of the incoming copies (N = 4) and by NVLink ingress (N = 8), not by the staging tile
   // (profiles/r02/multi_gpu.md) -- and 0.9 % slower on one GPU, so it is only built for experiments (variant 2).
   const bool two = variant == 2;
+  const int bal = fit_tc_balanced_rows(a.n, sm_count, variant);
+  if (bal > 0) {
+    MultiView b{};
+    b.bal_rows = bal;
+    return launch_variant<10, 1, false, true>(d, a, tl, pending_count, sm_count, s, n_tiles, n_chunks, b);
+  }
   return two ? launch_variant<8, 2, false>(d, a, tl, pending_count, sm_count, s, n_tiles, n_chunks, none)
              : launch_variant<10, 1, false>(d, a, tl, pending_count, sm_count, s, n_tiles, n_chunks, none);
 }

@@ -57,6 +57,7 @@ struct MultiView {                         // all null / 0 for an ordinary singl
   uint32_t* pending_by_cal;                // [n_cal]: rows per calendar the fast path left to the general pass
   int32_t n_cal;
   int32_t n_tiles;
+  int32_t bal_rows;                        // balanced single-calendar launch: rows per CTA (multiple of 8), else 0
 };
 
 // One series with gaps, handed to the thread-per-series solve kernel (256 B, indexed by row).
@@ -144,10 +145,13 @@ cudaError_t launch_predict_tc(const DesignView& d, const FitArgs& a, const Predi
 
 // TMA + tcgen05/TMEM kernel (fully observed fast path).  `tmap_y` / `tmap_at` are CUtensorMap blobs.
 struct TcLaunch {
-  alignas(64) unsigned char tmap_y[128];
+  alignas(64) unsigned char tmap_y[128];    // box {32 t, 128 series}
   alignas(64) unsigned char tmap_at[128];
+  alignas(64) unsigned char tmap_y8[128];   // box {32 t, 8 series}: the short last tile of a balanced launch's CTA
 };
-// variant: 0 = automatic, 1 = <10 smem stages, 1 forecast staging tile>, 2 = <8 stages, 2 staging tiles>
+// variant: 0 / 1 = <10 smem stages, 1 forecast staging tile>, tiles dealt round robin (the product), 2 = <8 stages,
+// 2 staging tiles>, 3 = balanced row ranges per CTA (both experiments that did not pay, kept for the record)
+int fit_tc_balanced_rows(int64_t n, int sm_count, int variant);
 cudaError_t launch_fit_tc(const DesignView& d, const FitArgs& a, const TcLaunch& tl,
                           uint32_t* pending_count, int sm_count, cudaStream_t s, int variant = 0,
                           const MultiView* multi = nullptr);

@@ -68,8 +68,9 @@ typedef struct mmf_config {
   int32_t device;          /* CUDA device ordinal, -1 = current device */
   int32_t kernel;          /* MMF_KERNEL_* */
   int32_t assume_finite;   /* 1: caller guarantees y has no NaN/Inf, skip the masked fix-up pass */
-  int32_t tc_variant;      /* tuning: 0 / 1 = the <10-stage, 1 staging tile> instantiation of the tcgen05 kernel, 2 = the
-                              experimental <8-stage, 2 staging tiles> one (same results) */
+  int32_t tc_variant;      /* tuning of the tcgen05 kernel, same results whichever: 0 / 1 = the product (128-row tiles dealt
+                              round robin over the SMs), 2 = the experimental <8-stage, 2 staging tiles> instantiation,
+                              3 = the experimental balanced launch (one row range per SM) -- DESIGN.md section 6 */
   int64_t chunk_series;    /* host-buffer path: series per pipelined chunk (0 = library default) */
   void*   stream;          /* cudaStream_t to enqueue on (NULL = library-owned stream) */
   int32_t host_narrow;     /* host-buffer path: 0 = automatic, 1 = always try, 2 = never: narrow float32 chunks to

@@ -581,3 +581,56 @@ def test_forecast_groups_many_calendars_holdout_mode_one_ragged_launch():
     assert np.array_equal(got["Demand"].to_numpy(), want["Demand"].to_numpy(), equal_nan=True)
     err = np.abs(got["Demand_Fitted"].to_numpy() - want["Demand_Fitted"].to_numpy())
     _le(err.max(), 40 * tolerance(df["Demand"].to_numpy()), "ragged holdout DataFrame batch vs per-group oracle UDF")
+
+
+# ---- balanced launches of small batches (fit_tc_kernel<.., BAL>) ---------------------------------------------
+@pytest.mark.parametrize("n", [1, 7, 8, 9, 127, 129, 1000, 10_000, 20_011])
+@pytest.mark.parametrize("mode", ["future", "holdout"])
+def test_balanced_launch_is_bit_equal_to_round_robin_tiles(n, mode):
+    """Small batches give every SM one contiguous row range (short last tile loaded as 8-row boxes) instead of
+    dealing 128-row tiles round robin.  Rows are independent in the GEMM: forecasts, coefficients and statuses must
+    be BIT-identical, with gaps, leading gaps and mostly-missing rows in the batch, and equal to the oracle's."""
+    import torch
+    t, h = 365, 28
+    yd, start = mmf.synth.daily_store_item_demand_torch(n, t, seed=77 + n, nan_frac=0.02)
+    yd[::5, :3] = float("nan")                   # leading gaps: general pass
+    if n > 3:
+        yd[3, 10:] = float("nan")                # (almost) empty row
+    y = yd.cpu().numpy()
+    got = {}
+    for variant in (1, 3):
+        eng = mmf.ForecastEngine(kernel="tc", tc_variant=variant)
+        res = mmf.forecast_packed(yd, start, "D", h, mode, engine=eng, want_status=True, want_beta=True)
+        torch.cuda.synchronize()
+        got[variant] = (res["pred"].cpu().numpy(), res["status"].cpu().numpy(), res["beta"].cpu().numpy())
+        eng.close()
+    assert np.array_equal(got[1][1], got[3][1])
+    assert np.array_equal(got[1][0], got[3][0], equal_nan=True)
+    assert np.array_equal(got[1][2], got[3][2], equal_nan=True)
+    want, wst = O.fit_forecast_packed_c(y, *_design(start, t, h, mode))
+    assert np.array_equal(got[3][1], wst)
+    ok = (wst == 0) & (np.arange(n) % 5 != 0) & (np.arange(n) != 3)      # ~7 scattered gaps: well conditioned
+    if ok.any():
+        _le(np.abs(got[3][0][ok] - want[ok]).max(), 4 * tolerance(y[ok]), (n, mode))
+
+
+def test_gappy_rows_do_not_depend_on_their_position_in_the_launch():
+    """A series' forecast must not depend on which tile of which SM it lands in.  With an odd number of 32-step chunks
+    (t_fit = 400 -> 13) the two transform groups of the tcgen05 kernel swap roles from one tile of a CTA to the next;
+    the gap positions are therefore filed by the chunk's parity inside the tile, not by the group that saw them, so the
+    solve applies them in one canonical order.  Rows of a CTA's SECOND tile, fit again as a batch of their own (first
+    tile of another CTA), must come out bit-identical -- with gaps."""
+    import torch
+    sm = torch.cuda.get_device_properties(0).multi_processor_count
+    t, h = 400, 28
+    n = sm * 128 + 3000
+    yd, start = mmf.synth.daily_store_item_demand_torch(n, t, seed=5, nan_frac=0.02)
+    eng = mmf.ForecastEngine(kernel="tc", tc_variant=1)
+    eng.plan_calendar(start, t, "D", h, "future")
+    whole = eng.fit_forecast(yd, t, h, want_status=True)
+    part = eng.fit_forecast(yd[sm * 128:], t, h, want_status=True)
+    torch.cuda.synchronize()
+    assert int((whole["status"] == 0).sum()) == n
+    assert torch.equal(whole["status"][sm * 128:], part["status"])
+    assert np.array_equal(whole["pred"][sm * 128:].cpu().numpy(), part["pred"].cpu().numpy())
+    eng.close()
