@@ -597,3 +597,58 @@ def test_device_packer_null_keys_null_dates_and_duplicates():
     dup = pa.Table.from_pandas(pd.concat([df, df.iloc[[5, 20]]], ignore_index=True), preserve_index=False)
     with pytest.raises(ValueError, match="duplicate"):
         pack_table_device(dup, freq="W-MON")
+
+
+def test_device_packer_equals_pandas_asfreq_on_random_frames():
+    """The device packer against pandas itself (what the reference runs per group, 02:422-423: sort_values + set_index +
+    asfreq): random groups, start dates, missing and off-grid dates, NaN demand, shuffled rows, daily and weekly grids."""
+    hyp = pytest.importorskip("hypothesis")
+    import pandas as pd
+    import pyarrow as pa
+    from mmf.packer import pack_table_device
+    st = hyp.strategies
+
+    @st.composite
+    def frames(draw):
+        freq = draw(st.sampled_from(["D", "W-MON"]))
+        step = 1 if freq == "D" else 7
+        rows = []
+        for gi in range(draw(st.integers(1, 6))):
+            start = dt.date(2021, 1, 4) + dt.timedelta(days=step * draw(st.integers(0, 30)))
+            n = draw(st.integers(1, 60))
+            keep = draw(st.lists(st.booleans(), min_size=n, max_size=n))
+            if not any(keep):
+                keep[0] = True
+            first, last = keep.index(True), n - 1 - keep[::-1].index(True)
+            for i in range(n):
+                if keep[i]:
+                    v = draw(st.one_of(st.integers(0, 60000).map(float), st.just(float("nan"))))
+                    rows.append(("P%d" % (gi % 2), "S%d" % gi, start + dt.timedelta(days=step * i), v))
+                    if step == 7 and first < i < last and draw(st.integers(0, 9)) == 0:
+                        rows.append(("P%d" % (gi % 2), "S%d" % gi, start + dt.timedelta(days=step * i + 2), 777.0))
+        order = draw(st.permutations(list(range(len(rows)))))
+        df = pd.DataFrame([rows[i] for i in order], columns=["Product", "SKU", "Date", "Demand"])
+        df["Date"] = pd.to_datetime(df["Date"]).dt.date
+        return freq, df.astype({"Demand": np.float32})
+
+    @hyp.settings(max_examples=40, deadline=None)
+    @hyp.given(frames())
+    def check(case):
+        freq, df = case
+        ref = df.assign(Date=pd.to_datetime(df["Date"]))
+        want = {}
+        for key, g in ref.groupby(["Product", "SKU"], sort=True):
+            s = g.sort_values("Date").set_index("Date")["Demand"].asfreq(freq)
+            want[key] = (str(s.index[0].date()), len(s), s.to_numpy(dtype=np.float32))
+        got = {}
+        for b in pack_table_device(pa.Table.from_pandas(df, preserve_index=False), freq=freq):
+            yb = b.y.cpu().numpy()
+            for r, key in enumerate(b.key_frame.itertuples(index=False)):
+                got[(key.Product, key.SKU)] = (str(b.start), b.t_len, yb[r, :b.t_len])
+        assert got.keys() == want.keys()
+        for key, (start, t_len, vals) in want.items():
+            gs, gt, gv = got[key]
+            assert (gs[:10], gt) == (start, t_len), key
+            assert np.array_equal(gv, vals, equal_nan=True), key
+
+    check()

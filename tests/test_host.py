@@ -235,3 +235,66 @@ def test_single_group_fast_path_equals_general_path():
     daily = pd.DataFrame({"store": "a", "item": "b", "d": pd.date_range("2021-03-01", periods=90, freq="D"),
                           "q": np.arange(90, dtype=np.float32)})
     both(daily, keys=("store", "item"), date_col="d", value_col="q", freq="D", horizon=14, mode="future")
+
+
+# ---- the packer against pandas itself: what the reference executes per group is sort_values + set_index + asfreq ----
+def _asfreq_reference(df, freq):
+    """02:422-423 verbatim in spirit, per group: the regular grid pandas builds and the values it leaves on it."""
+    out = {}
+    for key, g in df.groupby(["Product", "SKU"], sort=True):
+        s = g.sort_values("Date").set_index("Date")["Demand"].asfreq(freq)
+        out[key] = (s.index[0].date(), len(s), s.to_numpy(dtype=np.float32))
+    return out
+
+
+def test_packer_equals_pandas_asfreq_on_random_frames():
+    hyp = pytest.importorskip("hypothesis")
+    st = hyp.strategies
+
+    @st.composite
+    def frames(draw):
+        freq = draw(st.sampled_from(["D", "W-MON"]))
+        step = 1 if freq == "D" else 7
+        rows = []
+        for gi in range(draw(st.integers(1, 5))):
+            start = dt.date(2021, 1, 4) + dt.timedelta(days=step * draw(st.integers(0, 30)))     # a Monday
+            n = draw(st.integers(1, 40))
+            keep = draw(st.lists(st.booleans(), min_size=n, max_size=n))
+            if not any(keep):
+                keep[draw(st.integers(0, n - 1))] = True
+            first, last = keep.index(True), n - 1 - keep[::-1].index(True)
+            for i in range(n):
+                if keep[i]:
+                    v = draw(st.one_of(st.integers(0, 60000).map(float), st.just(float("nan"))))
+                    rows.append(("P%d" % (gi % 2), "S%d" % gi, start + dt.timedelta(days=step * i), v))
+                    if step == 7 and first < i < last and draw(st.integers(0, 9)) == 0:     # an off-grid row: asfreq drops it
+                        rows.append(("P%d" % (gi % 2), "S%d" % gi, start + dt.timedelta(days=step * i + 2), 777.0))
+        order = draw(st.permutations(list(range(len(rows)))))
+        df = pd.DataFrame([rows[i] for i in order], columns=["Product", "SKU", "Date", "Demand"])
+        df["Date"] = pd.to_datetime(df["Date"])
+        return freq, df
+
+    @hyp.settings(max_examples=60, deadline=None)
+    @hyp.given(frames())
+    def check(case):
+        freq, df = case
+        want = _asfreq_reference(df, freq)
+        got = {}
+        for b in mmf.pack_groups(df, freq=freq, pinned=False):
+            for r, key in enumerate(b.key_frame.itertuples(index=False)):
+                got[(key.Product, key.SKU)] = (b.start.astype("datetime64[D]").astype(object), b.t_len, np.array(b.y[r, :b.t_len]))
+        assert got.keys() == want.keys()
+        for key, (start, t_len, vals) in want.items():
+            gs, gt, gv = got[key]
+            assert (gs, gt) == (start, t_len), key
+            assert np.array_equal(gv, vals, equal_nan=True), key
+        import pyarrow as pa
+        table = pa.Table.from_pandas(df, preserve_index=False)
+        got2 = {}
+        for b in mmf.frames.pack_table_host(table, freq=freq, pinned=False):
+            for r, key in enumerate(b.key_frame.itertuples(index=False)):
+                got2[(key.Product, key.SKU)] = (b.t_len, np.array(b.y[r, :b.t_len]))
+        for key, (_, t_len, vals) in want.items():
+            assert got2[key][0] == t_len and np.array_equal(got2[key][1], vals, equal_nan=True), key
+
+    check()
