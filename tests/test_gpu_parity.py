@@ -631,7 +631,8 @@ def test_device_packer_equals_pandas_asfreq_on_random_frames():
         df["Date"] = pd.to_datetime(df["Date"]).dt.date
         return freq, df.astype({"Demand": np.float32})
 
-    @hyp.settings(max_examples=40, deadline=None)
+    @hyp.settings(max_examples=40, deadline=None, derandomize=True, database=None,
+                  suppress_health_check=list(hyp.HealthCheck))
     @hyp.given(frames())
     def check(case):
         freq, df = case

@@ -274,7 +274,8 @@ def test_packer_equals_pandas_asfreq_on_random_frames():
         df["Date"] = pd.to_datetime(df["Date"])
         return freq, df
 
-    @hyp.settings(max_examples=60, deadline=None)
+    @hyp.settings(max_examples=60, deadline=None, derandomize=True, database=None,
+                  suppress_health_check=list(hyp.HealthCheck))
     @hyp.given(frames())
     def check(case):
         freq, df = case
