@@ -534,7 +534,11 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e and args.mode == "future":
         ne = args.e2e_series or n
-        eng2 = mmf.ForecastEngine(device=local, kernel=args.kernel)
+        # host narrowing: the library's automatic setting turns it on only when the process sees ONE GPU (several ranks of a
+        # multi-GPU job would fight for host cores and memory bandwidth).  A single-process run on a multi-GPU box is the
+        # same situation as a single-GPU box, so it asks for it explicitly (mmf_config.host_narrow = 1, "always try");
+        # multi-rank runs keep the automatic setting.
+        eng2 = mmf.ForecastEngine(device=local, kernel=args.kernel, host_narrow=1 if world == 1 else 0)
         eng2.plan_calendar(start, t, "D", h, "future")
         yh = mmf.alloc_packed(ne, t)                      # pinned, pitched
         oh = mmf.pinned_empty((ne, h))
@@ -561,6 +565,8 @@ def run_ours(args):
                              "not used) while the previous chunk's copy is in flight, widened on the device"
                              if h2d_actual < ne * t * 4 else "float32 host buffer in, float32 over PCIe"),
                "api": "mmf_fit_forecast_f32 with pinned host float32 y/out (ForecastEngine.fit_forecast on NumPy arrays)",
+               "host_narrow": ("mmf_config.host_narrow = 1 (this is the only process feeding a GPU on this host)" if world == 1
+                               else "automatic (off when the process sees several GPUs)"),
                "cpu_affinity": (f"{len(numa_cpus)} cores local to the GPU (NVML)" if numa_cpus else "unchanged")}
         # the same end-to-end call when the demand column arrives as uint16 (the recipe's demand is integer valued,
         # 01-data-generator.py:304): half the H2D bytes, widened on the device, bit-equal forecasts required
