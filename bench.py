@@ -538,7 +538,7 @@ def run_ours(args):
         # multi-GPU job would fight for host cores and memory bandwidth).  A single-process run on a multi-GPU box is the
         # same situation as a single-GPU box, so it asks for it explicitly (mmf_config.host_narrow = 1, "always try");
         # multi-rank runs keep the automatic setting.
-        eng2 = mmf.ForecastEngine(device=local, kernel=args.kernel, host_narrow=1 if world == 1 else 0)
+        eng2 = mmf.ForecastEngine(device=local, kernel=args.kernel, host_narrow="on" if world == 1 else "auto")
         eng2.plan_calendar(start, t, "D", h, "future")
         yh = mmf.alloc_packed(ne, t)                      # pinned, pitched
         oh = mmf.pinned_empty((ne, h))
