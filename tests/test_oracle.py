@@ -276,3 +276,50 @@ def test_c_restatement_equals_numpy_oracle(oracle_golden):
     Xh = O.design_matrix(grid, 1067)
     got, _ = O.fit_forecast_packed_c(y2, Xh, 1067, 0, 1095)
     assert np.abs(got - oracle_golden["daily1095_holdout"]).max() < 1e-7
+
+
+def test_oracle_properties_on_random_series_and_masks():
+    """Size-independent properties of the model, checked on the oracle itself (NumPy route and C restatement) for random
+    lengths, horizons, scales and gap masks: shift equivariance f(y + c) = f(y) + c (the intercept is in the span),
+    linearity for a common mask f(a y + b z) = a f(y) + b f(z), exact reproduction of series that lie in the design's span,
+    and agreement of the two routes.  The GPU suite asserts the same properties at BASELINE sizes."""
+    hyp = pytest.importorskip("hypothesis")
+    st = hyp.strategies
+
+    @hyp.settings(max_examples=40, deadline=None, derandomize=True, database=None,
+                  suppress_health_check=list(hyp.HealthCheck))
+    @hyp.given(st.integers(60, 400), st.integers(1, 40), st.integers(0, 2**31 - 1), st.floats(0.0, 0.15),
+               st.sampled_from(["D", "W-MON"]))
+    def check(t, h, seed, gap_frac, freq):
+        rng = np.random.default_rng(seed)
+        grid = O.calendar_grid("2019-01-07", t + h, freq)
+        X = O.design_matrix(grid, t)
+        n = 6
+        y = (rng.uniform(100, 20000, (n, 1)) + rng.normal(0, 50, (n, t)) + rng.uniform(-3, 3, (n, 1)) * np.arange(t))
+        z = rng.uniform(0, 500, (n, t))
+        mask = rng.random((n, t)) < gap_frac
+        mask[:, 0] = False                                   # keep the centring value observed
+        ym, zm = np.where(mask, np.nan, y), np.where(mask, np.nan, z)
+        f = lambda a: O.fit_forecast_packed(a, X, t, t, h)   # noqa: E731
+        base, st0 = f(ym)
+        ok = st0 != 1                                        # status 1: no observed fit row (NaN out)
+        scale = np.abs(y).max()
+        shifted, _ = f(ym + 1234.5)
+        assert np.allclose(shifted[ok], base[ok] + 1234.5, rtol=0, atol=1e-7 * scale + 1e-6)
+        fz, st1 = f(zm)
+        lin, st2 = f(2.0 * ym - 3.0 * zm)
+        same = ok & (st0 == st1) & (st0 == st2)              # pivot dropping may differ only if a mask is degenerate
+        assert np.allclose(lin[same], 2.0 * base[same] - 3.0 * fz[same], rtol=0, atol=1e-6 * scale + 1e-5)
+        # a series in the span of the design (intercept + trend column) is reproduced exactly, gaps or not
+        line = 50.0 + 7.0 * X[:t, 1]
+        want = 50.0 + 7.0 * X[t:t + h, 1]
+        got, _ = f(np.where(mask[:1], np.nan, line[None, :]))
+        assert np.allclose(got[0], want, rtol=0, atol=1e-8 * (1 + np.abs(want).max()))
+        # the C restatement (float32 input) agrees with the NumPy route on the same float32 values
+        y32 = ym.astype(np.float32)
+        a, sa = O.fit_forecast_packed(y32.astype(np.float64), X, t, t, h)
+        b, sb = O.fit_forecast_packed_c(y32, X, t, t, h)
+        assert np.array_equal(sa, sb)
+        assert np.allclose(a, b, rtol=0, atol=1e-8 * scale + 1e-7, equal_nan=True)
+
+    check()
