@@ -52,6 +52,8 @@ class _OracleEngine:
 
     def plan_calendar(self, start, t_len, freq="D", horizon=28, mode="future", design="trend_season_exog"):
         if mode == "holdout":
+            if t_len - horizon < 1:
+                raise ValueError("series shorter than the forecast horizon")      # as ForecastEngine.plan_calendar
             self.t_fit, n_rows, ps, npred = t_len - horizon, t_len, 0, t_len
         else:
             self.t_fit, n_rows, ps, npred = t_len, t_len + horizon, t_len, horizon
@@ -299,3 +301,23 @@ def test_packer_equals_pandas_asfreq_on_random_frames():
             assert got2[key][0] == t_len and np.array_equal(got2[key][1], vals, equal_nan=True), key
 
     check()
+
+
+def test_groups_not_longer_than_the_horizon_fail_like_the_reference():
+    """A group with no more rows than ``forecast_horizon`` has nothing to train on: the reference's
+    ``split_train_score_data`` builds a mask of the wrong length / an empty train frame and the Spark task fails
+    (02:372-380, 441-450).  The engine's planning raises before any GPU work -- exercised here on the real
+    ``ForecastEngine`` methods without a context -- and ``forecast_groups`` lets the error through."""
+    eng = object.__new__(mmf.ForecastEngine)                 # planning checks its arguments before it touches the library
+    for t_len in (1, 5, 40):
+        with pytest.raises(ValueError, match="shorter than the forecast horizon"):
+            eng.plan_calendar("2021-01-04", t_len, "W-MON", 40, "holdout")
+    with pytest.raises(ValueError, match="shorter than the forecast horizon"):
+        eng.plan_calendars(["2021-01-04", "2021-01-04"], [200, 40], "W-MON", 40, "trend_season_exog", "holdout")
+    with pytest.raises(ValueError, match="mode must be"):
+        eng.plan_calendar("2021-01-04", 100, "W-MON", 40, "backtest")
+    short = _frame()                                         # 10 / 10 / 6 weekly rows per group
+    with pytest.raises(ValueError, match="shorter than the forecast horizon"):
+        mmf.forecast_groups(short, engine=_OracleEngine(), horizon=40, mode="holdout")
+    out = mmf.forecast_groups(short, engine=_OracleEngine(), horizon=40, mode="future")     # forecasting past the end is fine
+    assert len(out) == 3 * 40
